@@ -1,0 +1,147 @@
+/*
+ * rbk_knn.h — C ABI of the B200-native kNN engine behind RunbookAI's VectorStore.
+ *
+ * The reference has no FFI for this path; the seam is the TypeScript class
+ * `VectorStore` (src/knowledge/store/vector-store.ts:24-333), whose hot loop is
+ *     for (const [id, embedding] of this.embeddings)            (:210-215)
+ *         score = cosineSimilarity(queryEmbedding, embedding)   (embedder.ts:168-184)
+ *         if (score >= minScore) scored.push({id, score})
+ *     scored.sort((a,b) => b.score - a.score)                   (:218)
+ *     scored.slice(0, topK * 2)                                 (:221)
+ * Each entry point below names the reference lines it replaces.  A Node N-API addon
+ * (napi/rbk_napi.cc) or any other FFI binds exactly these symbols; INTEGRATION.md shows
+ * the binding.  Plain C types only: no C++/torch/CUDA types cross this boundary
+ * (CUDA streams and device pointers travel as void*).
+ *
+ * Conventions
+ *   - "slot" = dense insertion index of a row = the reference's Map insertion position
+ *     (SURVEY.md §8c S6/S9b).  The host side keeps the slot <-> "vec_<chunkId>" table.
+ *   - Every function returns rbk_status; on failure rbk_last_error() holds the message
+ *     the binding turns into `new Error(msg)`.  Nothing throws or aborts.
+ *   - Inputs are borrowed for the duration of the call; outputs are caller-allocated.
+ *   - An index is bound to ONE GPU.  A corpus sharded over several GPUs is one index
+ *     per GPU (one process per GPU, or several indexes in one process) plus
+ *     rbk_merge_topk_device() after the exchange of the per-shard lists.
+ *   - Thread safety: calls on the same index are serialised by an internal mutex;
+ *     different indexes are independent.
+ *   - There is NO CPU fallback: without a CUDA device rbk_index_create fails with
+ *     RBK_ECUDA.
+ */
+#ifndef RBK_KNN_H
+#define RBK_KNN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBK_ABI_VERSION 1
+/* Largest k_fetch a single search accepts (the scan keeps k_fetch + margin <= 128). */
+#define RBK_MAX_K_FETCH 112
+
+typedef struct rbk_index rbk_index;
+
+typedef enum {
+  RBK_OK = 0,
+  RBK_EINVAL = 1, /* bad argument */
+  RBK_ENOMEM = 2, /* host or device allocation failed */
+  RBK_ECUDA = 3,  /* CUDA runtime/driver error, or no device */
+  RBK_ENCCL = 4,  /* reserved for the in-library collective path */
+  RBK_EDIM = 5    /* "Vectors must have the same length" (embedder.ts:169-171) */
+} rbk_status;
+
+int rbk_abi_version(void);
+/* Message of the last failure on this thread (valid until the next failing call). */
+const char* rbk_last_error(void);
+
+/* ---- lifetime: `new VectorStore(dbPath)` / `close()` (vector-store.ts:28-32, :330) ---- */
+/* dim: embedding length (any d >= 1).  device: CUDA ordinal.  capacity_hint: rows to
+ * pre-allocate (0 = default); the index grows on demand. */
+rbk_status rbk_index_create(int32_t dim, int32_t device, int64_t capacity_hint, rbk_index** out);
+void rbk_index_destroy(rbk_index* idx); /* NULL is a no-op */
+
+/* Run all device work of this index on the given cudaStream_t (NULL = the index's own
+ * stream).  Lets a host framework time the engine with events on its current stream. */
+rbk_status rbk_index_set_stream(rbk_index* idx, void* cuda_stream);
+/* Global slot of local row 0 (row-sharded corpora).  Default 0. */
+rbk_status rbk_index_set_slot_base(rbk_index* idx, int64_t slot_base);
+
+/* ---- mutation: loadEmbeddings / addChunk(s) / deleteDocument / clear
+ *      (vector-store.ts:56-66, :93-183, :285-297, :322-325) ---- */
+/* rows: n_rows x dim, row-major.  f64 is the SQLite BLOB layout (little-endian float64,
+ * vector-store.ts:71-88).  Values are stored as bf16 (round-to-nearest-even); the index
+ * is exact for inputs representable in bf16.  first_slot_out (nullable)
+ * receives the LOCAL slot of the first appended row. */
+rbk_status rbk_index_append_f64(rbk_index* idx, const double* rows, int64_t n_rows, int64_t* first_slot_out);
+rbk_status rbk_index_append_f32(rbk_index* idx, const float* rows, int64_t n_rows, int64_t* first_slot_out);
+rbk_status rbk_index_append_bf16(rbk_index* idx, const uint16_t* rows, int64_t n_rows, int64_t* first_slot_out);
+/* Same, rows already in device memory on the index's GPU (bulk load without a PCIe hop). */
+rbk_status rbk_index_append_bf16_device(rbk_index* idx, const void* dev_rows, int64_t n_rows,
+                                        int64_t* first_slot_out);
+/* `this.embeddings.set(id, e)` on an existing id keeps its Map position (S9b). */
+rbk_status rbk_index_overwrite_f64(rbk_index* idx, int64_t local_slot, const double* row);
+/* `this.embeddings.delete(id)`: the rows stop matching; slots are not reused. */
+rbk_status rbk_index_tombstone(rbk_index* idx, const int64_t* local_slots, int64_t n);
+rbk_status rbk_index_clear(rbk_index* idx);
+int64_t rbk_index_count(const rbk_index* idx); /* live rows  */
+int64_t rbk_index_size(const rbk_index* idx);  /* slots used, tombstones included */
+int32_t rbk_index_dim(const rbk_index* idx);
+/* Copy stored rows back (bf16 bits), for tests and for reload sidecars. */
+rbk_status rbk_index_read_rows_bf16(rbk_index* idx, int64_t first_local_slot, int64_t n_rows, uint16_t* out);
+
+/* ---- search: the scan + sort + cut of VectorStore.search (vector-store.ts:207-221)
+ *      and findMostSimilar (embedder.ts:189-202), batched over B queries ---- */
+/*
+ * queries: B x query_dim row-major, HOST memory.  query_dim != dim -> RBK_EDIM, message
+ * "Vectors must have the same length".  For each query b the call returns the first
+ * out_counts[b] <= k_fetch entries of: all live rows with cosine >= min_score (fp64,
+ * inclusive; pass -INFINITY for "no threshold"), ordered by score descending, ties by
+ * ascending slot.  Scores are the reference's fp64 cosine, bit for bit, for the stored
+ * (bf16-exact) rows.  out_slots are GLOBAL (slot_base + local).  Unused tail entries of
+ * row b are slot -1 / score NaN.  kernel_ms_out (nullable): device time of the call.
+ */
+rbk_status rbk_index_search_f64(rbk_index* idx, const double* queries, int32_t B, int32_t query_dim,
+                                int32_t k_fetch, double min_score, int64_t* out_slots, double* out_scores,
+                                int32_t* out_counts, float* kernel_ms_out);
+rbk_status rbk_index_search_f32(rbk_index* idx, const float* queries, int32_t B, int32_t query_dim,
+                                int32_t k_fetch, double min_score, int64_t* out_slots, double* out_scores,
+                                int32_t* out_counts, float* kernel_ms_out);
+/* Device-resident variant: queries (f32, B x dim) and all outputs are device pointers on
+ * the index's GPU; work is enqueued on the index stream and the call returns after the
+ * exactness check of the batch (it synchronises the stream once). */
+rbk_status rbk_index_search_device(rbk_index* idx, const void* dev_queries_f32, int32_t B, int32_t k_fetch,
+                                   double min_score, void* dev_out_slots_i64, void* dev_out_scores_f64,
+                                   void* dev_out_counts_i32);
+
+/* Merge G per-shard result lists (layout [G][B][k_fetch], each sorted as above, device
+ * memory, e.g. the output of an all-gather) into [B][k_fetch] by (score desc, slot asc).
+ * Enqueued on cuda_stream; no synchronisation. */
+rbk_status rbk_merge_topk_device(int32_t device, void* cuda_stream, int32_t G, int32_t B, int32_t k_fetch,
+                                 const void* dev_slots_i64, const void* dev_scores_f64, const void* dev_counts_i32,
+                                 void* dev_out_slots_i64, void* dev_out_scores_f64, void* dev_out_counts_i32);
+
+/* ---- introspection ---- */
+typedef struct {
+  int64_t searches;         /* search calls */
+  int64_t queries;          /* queries answered */
+  int64_t fallback_queries; /* queries re-answered by the exhaustive fp64 kernel */
+  int64_t scan_launches;    /* launches of the fused scan kernel */
+  int64_t kernel_launches;  /* all kernel launches made by this index */
+  float last_scan_ms;       /* device time of the scan kernel(s) of the last search */
+  float last_total_ms;      /* device time of the whole last search */
+  int32_t last_kprime;      /* candidates kept per query by the last scan */
+  int32_t sm_count;
+} rbk_stats;
+rbk_status rbk_index_stats(const rbk_index* idx, rbk_stats* out);
+
+/* Debug/validation aid (tests only): run the scan on `queries` (host f32, B x dim) and
+ * return the approximate scores of every (query,row) pair, B x size() floats (host).
+ * NaN marks tombstoned/zero rows. */
+rbk_status rbk_index_debug_scores_f32(rbk_index* idx, const float* queries, int32_t B, float* out_scores);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBK_KNN_H */

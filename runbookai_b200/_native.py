@@ -1,0 +1,218 @@
+"""ctypes binding of include/rbk_knn.h — the same symbols the N-API addon binds.
+
+There is no fallback of any kind: if librbk_knn.so is missing this module raises at
+import, and if there is no CUDA device every index operation raises RbkError(RBK_ECUDA).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "librbk_knn.so"
+
+RBK_OK, RBK_EINVAL, RBK_ENOMEM, RBK_ECUDA, RBK_ENCCL, RBK_EDIM = range(6)
+RBK_MAX_K_FETCH = 112
+
+# every symbol include/rbk_knn.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    "rbk_abi_version", "rbk_last_error", "rbk_index_create", "rbk_index_destroy", "rbk_index_set_stream",
+    "rbk_index_set_slot_base", "rbk_index_append_f64", "rbk_index_append_f32", "rbk_index_append_bf16",
+    "rbk_index_append_bf16_device", "rbk_index_overwrite_f64", "rbk_index_tombstone", "rbk_index_clear",
+    "rbk_index_count", "rbk_index_size", "rbk_index_dim", "rbk_index_read_rows_bf16", "rbk_index_search_f64",
+    "rbk_index_search_f32", "rbk_index_search_device", "rbk_merge_topk_device", "rbk_index_stats",
+    "rbk_index_debug_scores_f32",
+]
+
+
+class RbkError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(message)
+        self.status = status
+
+
+class DimensionError(RbkError, ValueError):
+    """'Vectors must have the same length' (embedder.ts:169-171)."""
+
+
+class RbkStats(C.Structure):
+    _fields_ = [
+        ("searches", C.c_int64), ("queries", C.c_int64), ("fallback_queries", C.c_int64),
+        ("scan_launches", C.c_int64), ("kernel_launches", C.c_int64), ("last_scan_ms", C.c_float),
+        ("last_total_ms", C.c_float), ("last_kprime", C.c_int32), ("sm_count", C.c_int32),
+    ]
+
+
+def _load() -> C.CDLL:
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m runbookai_b200.build` "
+            "(or __graft_entry__.build()).  This engine has no CPU or library fallback.")
+    lib = C.CDLL(str(LIB_PATH))
+    vp, i32, i64, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    lib.rbk_abi_version.restype = C.c_int
+    lib.rbk_last_error.restype = C.c_char_p
+    lib.rbk_index_create.argtypes = [i32, i32, i64, C.POINTER(vp)]
+    lib.rbk_index_destroy.argtypes = [vp]
+    lib.rbk_index_destroy.restype = None
+    lib.rbk_index_set_stream.argtypes = [vp, vp]
+    lib.rbk_index_set_slot_base.argtypes = [vp, i64]
+    for n in ("rbk_index_append_f64", "rbk_index_append_f32", "rbk_index_append_bf16",
+              "rbk_index_append_bf16_device"):
+        getattr(lib, n).argtypes = [vp, vp, i64, C.POINTER(i64)]
+    lib.rbk_index_overwrite_f64.argtypes = [vp, i64, vp]
+    lib.rbk_index_tombstone.argtypes = [vp, vp, i64]
+    lib.rbk_index_clear.argtypes = [vp]
+    for n in ("rbk_index_count", "rbk_index_size"):
+        getattr(lib, n).argtypes = [vp]
+        getattr(lib, n).restype = i64
+    lib.rbk_index_dim.argtypes = [vp]
+    lib.rbk_index_dim.restype = i32
+    lib.rbk_index_read_rows_bf16.argtypes = [vp, i64, i64, vp]
+    for n in ("rbk_index_search_f64", "rbk_index_search_f32"):
+        getattr(lib, n).argtypes = [vp, vp, i32, i32, i32, f64, vp, vp, vp, C.POINTER(C.c_float)]
+    lib.rbk_index_search_device.argtypes = [vp, vp, i32, i32, f64, vp, vp, vp]
+    lib.rbk_merge_topk_device.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.rbk_index_stats.argtypes = [vp, C.POINTER(RbkStats)]
+    lib.rbk_index_debug_scores_f32.argtypes = [vp, vp, i32, vp]
+    return lib
+
+
+lib = _load()
+
+
+def check(status: int) -> None:
+    if status == RBK_OK:
+        return
+    msg = (lib.rbk_last_error() or b"").decode("utf-8", "replace")
+    if status == RBK_EDIM:
+        raise DimensionError(status, msg)
+    raise RbkError(status, msg)
+
+
+def ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Index:
+    """Thin object wrapper over rbk_index* (one GPU shard)."""
+
+    def __init__(self, dim: int, device: int = 0, capacity_hint: int = 0):
+        self._h = None
+        h = C.c_void_p()
+        check(lib.rbk_index_create(dim, device, capacity_hint, C.byref(h)))
+        self._h = h
+        self.dim = dim
+        self.device = device
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib.rbk_index_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- configuration
+    def set_stream(self, cuda_stream: int | None) -> None:
+        check(lib.rbk_index_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def set_slot_base(self, base: int) -> None:
+        check(lib.rbk_index_set_slot_base(self._h, base))
+
+    # -- mutation
+    def _append(self, fn, rows: np.ndarray) -> int:
+        if rows.ndim != 2 or rows.shape[1] != self.dim:
+            raise DimensionError(RBK_EDIM, "Vectors must have the same length")
+        first = C.c_int64(-1)
+        check(fn(self._h, ptr(rows), rows.shape[0], C.byref(first)))
+        return first.value
+
+    def append_f64(self, rows) -> int:
+        return self._append(lib.rbk_index_append_f64, np.ascontiguousarray(rows, dtype=np.float64))
+
+    def append_f32(self, rows) -> int:
+        return self._append(lib.rbk_index_append_f32, np.ascontiguousarray(rows, dtype=np.float32))
+
+    def append_bf16(self, rows_u16) -> int:
+        return self._append(lib.rbk_index_append_bf16, np.ascontiguousarray(rows_u16, dtype=np.uint16))
+
+    def append_bf16_device(self, dev_ptr: int, n_rows: int) -> int:
+        first = C.c_int64(-1)
+        check(lib.rbk_index_append_bf16_device(self._h, C.c_void_p(dev_ptr), n_rows, C.byref(first)))
+        return first.value
+
+    def overwrite_f64(self, slot: int, row) -> None:
+        r = np.ascontiguousarray(row, dtype=np.float64)
+        if r.shape != (self.dim,):
+            raise DimensionError(RBK_EDIM, "Vectors must have the same length")
+        check(lib.rbk_index_overwrite_f64(self._h, slot, ptr(r)))
+
+    def tombstone(self, slots) -> None:
+        s = np.ascontiguousarray(slots, dtype=np.int64)
+        check(lib.rbk_index_tombstone(self._h, ptr(s), s.shape[0]))
+
+    def clear(self) -> None:
+        check(lib.rbk_index_clear(self._h))
+
+    def count(self) -> int:
+        return lib.rbk_index_count(self._h)
+
+    def size(self) -> int:
+        return lib.rbk_index_size(self._h)
+
+    def read_rows_bf16(self, first: int, n: int) -> np.ndarray:
+        out = np.empty((n, self.dim), dtype=np.uint16)
+        check(lib.rbk_index_read_rows_bf16(self._h, first, n, ptr(out)))
+        return out
+
+    # -- search
+    def search(self, queries, k_fetch: int, min_score: float | None = 0.5):
+        """Returns (slots int64 [B,k], scores float64 [B,k], counts int32 [B], device_ms)."""
+        q = np.asarray(queries)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.dtype == np.float32:
+            q = np.ascontiguousarray(q)
+            fn = lib.rbk_index_search_f32
+        else:
+            q = np.ascontiguousarray(q, dtype=np.float64)
+            fn = lib.rbk_index_search_f64
+        B = q.shape[0]
+        slots = np.empty((B, k_fetch), dtype=np.int64)
+        scores = np.empty((B, k_fetch), dtype=np.float64)
+        counts = np.empty((B,), dtype=np.int32)
+        ms = C.c_float(0)
+        ms_arg = -np.inf if min_score is None else float(min_score)
+        check(fn(self._h, ptr(q), B, q.shape[1], k_fetch, ms_arg, ptr(slots), ptr(scores), ptr(counts), C.byref(ms)))
+        return slots, scores, counts, ms.value
+
+    def search_device(self, q_ptr: int, B: int, k_fetch: int, min_score: float | None, slots_ptr: int,
+                      scores_ptr: int, counts_ptr: int) -> None:
+        ms_arg = -np.inf if min_score is None else float(min_score)
+        check(lib.rbk_index_search_device(self._h, C.c_void_p(q_ptr), B, k_fetch, ms_arg, C.c_void_p(slots_ptr),
+                                          C.c_void_p(scores_ptr), C.c_void_p(counts_ptr)))
+
+    def debug_scores(self, queries_f32) -> np.ndarray:
+        q = np.ascontiguousarray(queries_f32, dtype=np.float32)
+        out = np.empty((q.shape[0], self.size()), dtype=np.float32)
+        check(lib.rbk_index_debug_scores_f32(self._h, ptr(q), q.shape[0], ptr(out)))
+        return out
+
+    def stats(self) -> dict:
+        st = RbkStats()
+        check(lib.rbk_index_stats(self._h, C.byref(st)))
+        return {f: getattr(st, f) for f, _ in RbkStats._fields_}
+
+
+def merge_topk_device(device: int, stream: int, G: int, B: int, k_fetch: int, slots_ptr: int, scores_ptr: int,
+                      counts_ptr: int, out_slots_ptr: int, out_scores_ptr: int, out_counts_ptr: int) -> None:
+    check(lib.rbk_merge_topk_device(device, C.c_void_p(stream), G, B, k_fetch, C.c_void_p(slots_ptr),
+                                    C.c_void_p(scores_ptr), C.c_void_p(counts_ptr), C.c_void_p(out_slots_ptr),
+                                    C.c_void_p(out_scores_ptr), C.c_void_p(out_counts_ptr)))

@@ -1,0 +1,756 @@
+// rbk_capi.cu — the C ABI of include/rbk_knn.h: index lifetime, mutation, batched search.
+// Host-side orchestration only; the device work is in rbk_ingest.cu / rbk_scan.cu /
+// rbk_finalize.cu.  No torch, no CPU compute path: every entry point that needs a GPU
+// fails with RBK_ECUDA when there is none.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rbk_knn.h"
+#include "rbk_internal.h"
+
+using namespace rbk;
+
+namespace {
+
+thread_local std::string g_err;
+
+rbk_status fail(rbk_status st, const std::string& msg) {
+  g_err = msg;
+  return st;
+}
+rbk_status cuda_fail(cudaError_t e, const char* what) {
+  // a sticky error (trap in a kernel) poisons the context; report it verbatim
+  return fail(e == cudaErrorMemoryAllocation ? RBK_ENOMEM : RBK_ECUDA,
+              std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+#define CK(expr)                                         \
+  do {                                                   \
+    cudaError_t _e = (expr);                             \
+    if (_e != cudaSuccess) return cuda_fail(_e, #expr);  \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2D bf16 row-major [rows][dpad] tensor, box = 64 columns (128 B, one swizzle row) x box_rows.
+rbk_status encode_rows_tmap(CUtensorMap* out, const void* base, int64_t rows, int dpad, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(RBK_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(dpad), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(dpad) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed: CUresult %d (rows=%lld dpad=%d)", (int)r,
+             (long long)rows, dpad);
+    return fail(RBK_ECUDA, buf);
+  }
+  return RBK_OK;
+}
+
+int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t ensure(size_t want) {
+    if (want <= n) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T));
+    if (e == cudaSuccess) n = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+template <typename T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t ensure(size_t want) {
+    if (want <= n) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
+    cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&p), want * sizeof(T));
+    if (e == cudaSuccess) n = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+}  // namespace
+
+struct rbk_index {
+  int dim = 0, dpad = 0, device = 0, sm_count = 0, margin = 16;
+  int64_t cap = 0, n_rows = 0, n_live = 0, slot_base = 0;
+  uint16_t* rows = nullptr;
+  float* inv_norm = nullptr;  // padded to a multiple of kBlockN (+ one tile), NaN-filled
+  double* norm2 = nullptr;
+  unsigned int* dead_bits = nullptr;
+  int* d_counter = nullptr;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  std::mutex mu;
+  // ingest staging
+  DevBuf<unsigned char> stage;
+  DevBuf<int64_t> d_slots;
+  // search scratch
+  DevBuf<unsigned char> q_raw;
+  DevBuf<uint16_t> q_bf16;
+  DevBuf<double> q_f64, q_norm2, q_eps;
+  DevBuf<float> q_inv_norm, thr_init;
+  DevBuf<unsigned long long> cand;
+  DevBuf<int> cand_cnt, flags, fail_list, o_counts, part_rows, part_cnt;
+  DevBuf<long long> o_slots;
+  DevBuf<double> o_scores, part_scores;
+  DevBuf<float> dbg;
+  PinBuf<int> h_flags, h_counts;
+  PinBuf<long long> h_slots;
+  PinBuf<double> h_scores;
+  PinBuf<float> h_f32;
+  CUtensorMap tmap_c;
+  const void* tmap_c_base = nullptr;
+  int64_t tmap_c_rows = -1;
+  std::vector<cudaEvent_t> ev;
+  rbk_stats stats;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+cudaEvent_t get_event(rbk_index* ix, size_t i) {
+  while (ix->ev.size() <= i) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    ix->ev.push_back(e);
+  }
+  return ix->ev[i];
+}
+
+int64_t inv_norm_len(int64_t cap) { return round_up(cap, kBlockN) + kBlockN; }
+
+rbk_status ensure_capacity(rbk_index* ix, int64_t need) {
+  if (need <= ix->cap) return RBK_OK;
+  if (need >= (1ll << 31) - 2 * kBlockN) return fail(RBK_EINVAL, "an index shard holds at most 2^31 rows");
+  int64_t ncap = std::max<int64_t>(need, std::max<int64_t>(ix->cap * 2, 1024));
+  uint16_t* rows = nullptr;
+  float* inv = nullptr;
+  double* n2 = nullptr;
+  unsigned int* dead = nullptr;
+  const size_t dead_words = static_cast<size_t>((ncap + 31) / 32);
+  cudaError_t e;
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&rows), static_cast<size_t>(ncap) * ix->dpad * 2)) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&inv), static_cast<size_t>(inv_norm_len(ncap)) * 4)) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&n2), static_cast<size_t>(ncap) * 8)) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&dead), dead_words * 4)) != cudaSuccess) {
+    cudaFree(rows);
+    cudaFree(inv);
+    cudaFree(n2);
+    cudaFree(dead);
+    return cuda_fail(e, "cudaMalloc(index storage)");
+  }
+  cudaStream_t st = ix->stream;
+  CK(cudaMemsetAsync(inv, 0xFF, static_cast<size_t>(inv_norm_len(ncap)) * 4, st));  // all-ones = NaN
+  CK(cudaMemsetAsync(dead, 0, dead_words * 4, st));
+  if (ix->n_rows > 0) {
+    CK(cudaMemcpyAsync(rows, ix->rows, static_cast<size_t>(ix->n_rows) * ix->dpad * 2, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(inv, ix->inv_norm, static_cast<size_t>(ix->n_rows) * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(n2, ix->norm2, static_cast<size_t>(ix->n_rows) * 8, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(dead, ix->dead_bits, static_cast<size_t>((ix->n_rows + 31) / 32) * 4,
+                       cudaMemcpyDeviceToDevice, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  cudaFree(ix->rows);
+  cudaFree(ix->inv_norm);
+  cudaFree(ix->norm2);
+  cudaFree(ix->dead_bits);
+  ix->rows = rows;
+  ix->inv_norm = inv;
+  ix->norm2 = n2;
+  ix->dead_bits = dead;
+  ix->cap = ncap;
+  return RBK_OK;
+}
+
+// src: host (is_device = false) or device rows of `elem` bytes (8 = f64, 4 = f32, 2 = bf16).
+rbk_status append_rows(rbk_index* ix, const void* src, bool is_device, int elem, int64_t n, int64_t* first_out) {
+  if (!ix) return fail(RBK_EINVAL, "null index");
+  if (n < 0 || (n > 0 && !src)) return fail(RBK_EINVAL, "bad rows argument");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard dg(ix->device);
+  if (first_out) *first_out = ix->n_rows;
+  if (n == 0) return RBK_OK;
+  rbk_status st = ensure_capacity(ix, ix->n_rows + n);
+  if (st != RBK_OK) return st;
+  const int src_type = elem == 8 ? 0 : (elem == 4 ? 1 : 2);
+  uint16_t* dst0 = ix->rows + static_cast<size_t>(ix->n_rows) * ix->dpad;
+  if (is_device) {
+    if (elem == 2 && ix->dpad == ix->dim) {
+      CK(cudaMemcpyAsync(dst0, src, static_cast<size_t>(n) * ix->dim * 2, cudaMemcpyDeviceToDevice, ix->stream));
+    } else {
+      CK(launch_convert_rows(src, src_type, n, ix->dim, ix->dpad, dst0, ix->stream));
+      ix->stats.kernel_launches++;
+    }
+  } else {
+    const size_t row_bytes = static_cast<size_t>(ix->dim) * elem;
+    const int64_t chunk_rows = std::max<int64_t>(1, std::min<int64_t>(n, (64ll << 20) / static_cast<int64_t>(row_bytes)));
+    CK(ix->stage.ensure(static_cast<size_t>(chunk_rows) * row_bytes));
+    for (int64_t r0 = 0; r0 < n; r0 += chunk_rows) {
+      const int64_t nr = std::min<int64_t>(chunk_rows, n - r0);
+      const unsigned char* hp = static_cast<const unsigned char*>(src) + static_cast<size_t>(r0) * row_bytes;
+      CK(cudaMemcpyAsync(ix->stage.p, hp, static_cast<size_t>(nr) * row_bytes, cudaMemcpyHostToDevice, ix->stream));
+      CK(launch_convert_rows(ix->stage.p, src_type, nr, ix->dim, ix->dpad, dst0 + static_cast<size_t>(r0) * ix->dpad,
+                             ix->stream));
+      ix->stats.kernel_launches++;
+      // the staging buffer is reused by the next chunk; pageable H2D copies are already
+      // synchronous with respect to the host buffer, the kernel is ordered by the stream
+    }
+  }
+  CK(launch_row_norms(dst0, n, ix->dim, ix->dpad, ix->inv_norm + ix->n_rows, ix->norm2 + ix->n_rows, ix->stream));
+  ix->stats.kernel_launches++;
+  CK(cudaStreamSynchronize(ix->stream));
+  ix->n_rows += n;
+  ix->n_live += n;
+  return RBK_OK;
+}
+
+int pick_kprime(const rbk_index* ix, int k_fetch) {
+  int kp = static_cast<int>(round_up(k_fetch + ix->margin, 16));
+  return std::min(kp, kMaxKPrime);
+}
+
+rbk_status refresh_corpus_tmap(rbk_index* ix) {
+  if (ix->tmap_c_base == ix->rows && ix->tmap_c_rows == ix->n_rows) return RBK_OK;
+  rbk_status st = encode_rows_tmap(&ix->tmap_c, ix->rows, ix->n_rows, ix->dpad, kBlockN);
+  if (st != RBK_OK) return st;
+  ix->tmap_c_base = ix->rows;
+  ix->tmap_c_rows = ix->n_rows;
+  return RBK_OK;
+}
+
+rbk_status ensure_query_scratch(rbk_index* ix, int B, int elem) {
+  CK(ix->q_raw.ensure(static_cast<size_t>(B) * ix->dim * elem));
+  CK(ix->q_bf16.ensure(static_cast<size_t>(B) * ix->dpad));
+  CK(ix->q_f64.ensure(static_cast<size_t>(B) * ix->dim));
+  CK(ix->q_norm2.ensure(B));
+  CK(ix->q_eps.ensure(B));
+  CK(ix->q_inv_norm.ensure(B));
+  CK(ix->thr_init.ensure(B));
+  CK(ix->flags.ensure(B));
+  CK(ix->cand.ensure(static_cast<size_t>(ix->sm_count) * kBlockM * kListCap));
+  CK(ix->cand_cnt.ensure(static_cast<size_t>(ix->sm_count) * kBlockM));
+  return RBK_OK;
+}
+
+QueryBuffers query_buffers(rbk_index* ix, int q0) {
+  QueryBuffers qb;
+  qb.q_bf16 = ix->q_bf16.p + static_cast<size_t>(q0) * ix->dpad;
+  qb.q_f64 = ix->q_f64.p + static_cast<size_t>(q0) * ix->dim;
+  qb.q_norm2 = ix->q_norm2.p + q0;
+  qb.q_inv_norm = ix->q_inv_norm.p + q0;
+  qb.q_eps = ix->q_eps.p + q0;
+  qb.thr_init = ix->thr_init.p + q0;
+  return qb;
+}
+
+// Launch the scan (+ optionally finalize) for every sub-batch.  d_q: device queries.
+rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_fetch, double min_score,
+                    long long* d_slots, double* d_scores, int* d_counts, float* dbg, size_t* ev_cursor) {
+  const int kprime = pick_kprime(ix, k_fetch);
+  ix->stats.last_kprime = kprime;
+  CK(launch_prep_queries(d_q, src_type, B, ix->dim, ix->dpad, min_score, query_buffers(ix, 0), ix->stream));
+  ix->stats.kernel_launches++;
+  if (ix->n_rows == 0) {
+    // nothing to scan: finalize would read unwritten lists; emit empty results directly
+    if (d_counts) {
+      CK(cudaMemsetAsync(d_counts, 0, sizeof(int) * B, ix->stream));
+      CK(cudaMemsetAsync(d_slots, 0xFF, sizeof(long long) * B * k_fetch, ix->stream));   // -1
+      CK(cudaMemsetAsync(d_scores, 0xFF, sizeof(double) * B * k_fetch, ix->stream));     // NaN
+      CK(cudaMemsetAsync(ix->flags.p, 0, sizeof(int) * B, ix->stream));
+    }
+    return RBK_OK;
+  }
+  rbk_status st = refresh_corpus_tmap(ix);
+  if (st != RBK_OK) return st;
+  const int n_tiles = static_cast<int>((ix->n_rows + kBlockN - 1) / kBlockN);
+  for (int q0 = 0; q0 < B; q0 += kMaxSubBatch) {
+    const int Bs = std::min(kMaxSubBatch, B - q0);
+    const int QB = (Bs + kBlockM - 1) / kBlockM;
+    int R = std::max(1, std::min(ix->sm_count / QB, n_tiles));
+    CUtensorMap tmap_q;
+    st = encode_rows_tmap(&tmap_q, ix->q_bf16.p + static_cast<size_t>(q0) * ix->dpad, Bs, ix->dpad, kBlockM);
+    if (st != RBK_OK) return st;
+    ScanParams sp;
+    sp.inv_norm_c = ix->inv_norm;
+    sp.thr_init = ix->thr_init.p + q0;
+    sp.cand = ix->cand.p;
+    sp.cand_cnt = ix->cand_cnt.p;
+    sp.dbg_scores = dbg ? dbg + static_cast<size_t>(q0) * ix->n_rows : nullptr;
+    sp.n_rows = static_cast<int>(ix->n_rows);
+    sp.B = Bs;
+    sp.kprime = kprime;
+    sp.num_kb = (ix->dpad + kBlockK - 1) / kBlockK;
+    sp.QB = QB;
+    sp.R = R;
+    sp.n_tiles = n_tiles;
+    CK(cudaEventRecord(get_event(ix, (*ev_cursor)++), ix->stream));
+    CK(launch_scan(tmap_q, ix->tmap_c, sp, ix->stream));
+    CK(cudaEventRecord(get_event(ix, (*ev_cursor)++), ix->stream));
+    ix->stats.scan_launches++;
+    ix->stats.kernel_launches++;
+    if (d_counts) {
+      FinalizeParams fp;
+      fp.cand = ix->cand.p;
+      fp.cand_cnt = ix->cand_cnt.p;
+      fp.QB = QB;
+      fp.R = R;
+      fp.kprime = kprime;
+      fp.k_fetch = k_fetch;
+      fp.B = Bs;
+      fp.d = ix->dim;
+      fp.dpad = ix->dpad;
+      fp.q0 = q0;
+      fp.min_score = min_score;
+      fp.rows = ix->rows;
+      fp.row_norm2 = ix->norm2;
+      fp.n_rows = ix->n_rows;
+      fp.slot_base = ix->slot_base;
+      fp.q = query_buffers(ix, q0);
+      fp.out_slots = d_slots + static_cast<size_t>(q0) * k_fetch;
+      fp.out_scores = d_scores + static_cast<size_t>(q0) * k_fetch;
+      fp.out_counts = d_counts + q0;
+      fp.flags = ix->flags.p + q0;
+      CK(launch_finalize(fp, ix->stream));
+      ix->stats.kernel_launches++;
+    }
+  }
+  return RBK_OK;
+}
+
+rbk_status run_fallback(rbk_index* ix, const std::vector<int>& fails, int k_fetch, double min_score,
+                        long long* d_slots, double* d_scores, int* d_counts) {
+  const int nf = static_cast<int>(fails.size());
+  const int nb = std::max(1, std::min<int>(ix->sm_count * 2, static_cast<int>((ix->n_rows + 255) / 256)));
+  CK(ix->fail_list.ensure(nf));
+  CK(ix->part_scores.ensure(static_cast<size_t>(nf) * nb * k_fetch));
+  CK(ix->part_rows.ensure(static_cast<size_t>(nf) * nb * k_fetch));
+  CK(ix->part_cnt.ensure(static_cast<size_t>(nf) * nb));
+  CK(cudaMemcpyAsync(ix->fail_list.p, fails.data(), sizeof(int) * nf, cudaMemcpyHostToDevice, ix->stream));
+  ExactParams ep;
+  ep.fail_list = ix->fail_list.p;
+  ep.n_fail = nf;
+  ep.d = ix->dim;
+  ep.dpad = ix->dpad;
+  ep.k_fetch = k_fetch;
+  ep.min_score = min_score;
+  ep.rows = ix->rows;
+  ep.row_norm2 = ix->norm2;
+  ep.inv_norm_c = ix->inv_norm;
+  ep.n_rows = ix->n_rows;
+  ep.slot_base = ix->slot_base;
+  ep.q_f64 = ix->q_f64.p;
+  ep.q_norm2 = ix->q_norm2.p;
+  ep.part_scores = ix->part_scores.p;
+  ep.part_rows = ix->part_rows.p;
+  ep.part_cnt = ix->part_cnt.p;
+  ep.n_blocks = nb;
+  ep.out_slots = d_slots;
+  ep.out_scores = d_scores;
+  ep.out_counts = d_counts;
+  CK(launch_exact_fallback(ep, ix->stream));
+  // pageable source: the copy above has completed its host read before returning
+  ix->stats.kernel_launches += 2;
+  ix->stats.fallback_queries += nf;
+  return RBK_OK;
+}
+
+// Whole search.  q_host/q_dev: exactly one is non-null.  Host outputs (h_*) may be null
+// (device-output variant); device outputs may be null (host variant uses index scratch).
+rbk_status search_core(rbk_index* ix, const void* q_host, const void* q_dev, int elem, int B, int query_dim,
+                       int k_fetch, double min_score, long long* d_slots, double* d_scores, int* d_counts,
+                       int64_t* h_slots, double* h_scores, int32_t* h_counts, float* ms_out) {
+  if (!ix) return fail(RBK_EINVAL, "null index");
+  if (B < 0 || (B > 0 && !q_host && !q_dev)) return fail(RBK_EINVAL, "bad queries argument");
+  if (k_fetch < 1 || k_fetch > RBK_MAX_K_FETCH) return fail(RBK_EINVAL, "k_fetch must be in [1, 112]");
+  if (query_dim != ix->dim) return fail(RBK_EDIM, "Vectors must have the same length");  // embedder.ts:170
+  if (min_score != min_score) return fail(RBK_EINVAL, "min_score is NaN");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard dg(ix->device);
+  ix->stats.searches++;
+  if (ms_out) *ms_out = 0.f;
+  if (B == 0) return RBK_OK;
+  rbk_status st = ensure_query_scratch(ix, B, elem);
+  if (st != RBK_OK) return st;
+  const size_t nout = static_cast<size_t>(B) * k_fetch;
+  if (!d_slots) {
+    CK(ix->o_slots.ensure(nout));
+    CK(ix->o_scores.ensure(nout));
+    CK(ix->o_counts.ensure(B));
+    d_slots = ix->o_slots.p;
+    d_scores = ix->o_scores.p;
+    d_counts = ix->o_counts.p;
+  }
+  CK(ix->h_flags.ensure(B));
+  if (h_slots) {
+    CK(ix->h_slots.ensure(nout));
+    CK(ix->h_scores.ensure(nout));
+    CK(ix->h_counts.ensure(B));
+  }
+  size_t evc = 2;
+  CK(cudaEventRecord(get_event(ix, 0), ix->stream));
+  const void* d_q = q_dev;
+  if (q_host) {
+    CK(cudaMemcpyAsync(ix->q_raw.p, q_host, static_cast<size_t>(B) * ix->dim * elem, cudaMemcpyHostToDevice,
+                       ix->stream));
+    d_q = ix->q_raw.p;
+  }
+  st = run_scan(ix, d_q, elem == 8 ? 0 : 1, B, k_fetch, min_score, d_slots, d_scores, d_counts, nullptr, &evc);
+  if (st != RBK_OK) return st;
+  CK(cudaMemcpyAsync(ix->h_flags.p, ix->flags.p, sizeof(int) * B, cudaMemcpyDeviceToHost, ix->stream));
+  auto copy_results = [&]() -> cudaError_t {
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(ix->h_slots.p, d_slots, sizeof(long long) * nout, cudaMemcpyDeviceToHost, ix->stream)))
+      return e;
+    if ((e = cudaMemcpyAsync(ix->h_scores.p, d_scores, sizeof(double) * nout, cudaMemcpyDeviceToHost, ix->stream)))
+      return e;
+    return cudaMemcpyAsync(ix->h_counts.p, d_counts, sizeof(int) * B, cudaMemcpyDeviceToHost, ix->stream);
+  };
+  if (h_slots) CK(copy_results());
+  CK(cudaEventRecord(get_event(ix, 1), ix->stream));
+  CK(cudaStreamSynchronize(ix->stream));
+  std::vector<int> fails;
+  for (int b = 0; b < B; ++b)
+    if (ix->h_flags.p[b]) fails.push_back(b);
+  if (!fails.empty()) {
+    st = run_fallback(ix, fails, k_fetch, min_score, d_slots, d_scores, d_counts);
+    if (st != RBK_OK) return st;
+    if (h_slots) CK(copy_results());
+    CK(cudaEventRecord(get_event(ix, 1), ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+  }
+  float total = 0.f, scan = 0.f;
+  cudaEventElapsedTime(&total, get_event(ix, 0), get_event(ix, 1));
+  for (size_t i = 2; i + 1 < evc; i += 2) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, get_event(ix, i), get_event(ix, i + 1));
+    scan += t;
+  }
+  ix->stats.last_total_ms = total;
+  ix->stats.last_scan_ms = scan;
+  ix->stats.queries += B;
+  if (ms_out) *ms_out = total;
+  if (h_slots) {
+    memcpy(h_slots, ix->h_slots.p, sizeof(int64_t) * nout);
+    memcpy(h_scores, ix->h_scores.p, sizeof(double) * nout);
+    memcpy(h_counts, ix->h_counts.p, sizeof(int32_t) * B);
+  }
+  return RBK_OK;
+}
+
+}  // namespace
+
+// =========================================================================== C ABI
+extern "C" {
+
+int rbk_abi_version(void) { return RBK_ABI_VERSION; }
+const char* rbk_last_error(void) { return g_err.c_str(); }
+
+rbk_status rbk_index_create(int32_t dim, int32_t device, int64_t capacity_hint, rbk_index** out) {
+  if (!out) return fail(RBK_EINVAL, "out is null");
+  *out = nullptr;
+  if (dim < 1 || dim > (1 << 20)) return fail(RBK_EINVAL, "dim out of range");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(RBK_ECUDA, std::string("no CUDA device (this engine has no CPU path): ") +
+                               (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  if (device < 0 || device >= ndev) return fail(RBK_EINVAL, "device ordinal out of range");
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(RBK_ECUDA, std::string("this build targets sm_100a (Blackwell B200); device is ") + prop.name);
+  DeviceGuard dg(device);
+  rbk_index* ix = new (std::nothrow) rbk_index();
+  if (!ix) return fail(RBK_ENOMEM, "out of host memory");
+  ix->dim = dim;
+  ix->dpad = static_cast<int>(round_up(dim, 8));
+  ix->device = device;
+  ix->sm_count = prop.multiProcessorCount;
+  memset(&ix->stats, 0, sizeof ix->stats);
+  ix->stats.sm_count = ix->sm_count;
+  if (const char* m = getenv("RBK_KNN_MARGIN")) ix->margin = std::max(0, std::min(96, atoi(m)));
+  e = cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete ix;
+    return cuda_fail(e, "cudaStreamCreate");
+  }
+  ix->stream = ix->own_stream;
+  e = cudaMalloc(reinterpret_cast<void**>(&ix->d_counter), sizeof(int));
+  if (e != cudaSuccess) {
+    rbk_index_destroy(ix);
+    return cuda_fail(e, "cudaMalloc");
+  }
+  rbk_status st = ensure_capacity(ix, std::max<int64_t>(capacity_hint, 1024));
+  if (st != RBK_OK) {
+    rbk_index_destroy(ix);
+    return st;
+  }
+  *out = ix;
+  return RBK_OK;
+}
+
+void rbk_index_destroy(rbk_index* ix) {
+  if (!ix) return;
+  {
+    DeviceGuard dg(ix->device);
+    if (ix->stream) cudaStreamSynchronize(ix->stream);
+    cudaFree(ix->rows);
+    cudaFree(ix->inv_norm);
+    cudaFree(ix->norm2);
+    cudaFree(ix->dead_bits);
+    cudaFree(ix->d_counter);
+    ix->stage.release();
+    ix->d_slots.release();
+    ix->q_raw.release();
+    ix->q_bf16.release();
+    ix->q_f64.release();
+    ix->q_norm2.release();
+    ix->q_eps.release();
+    ix->q_inv_norm.release();
+    ix->thr_init.release();
+    ix->cand.release();
+    ix->cand_cnt.release();
+    ix->flags.release();
+    ix->fail_list.release();
+    ix->o_counts.release();
+    ix->part_rows.release();
+    ix->part_cnt.release();
+    ix->o_slots.release();
+    ix->o_scores.release();
+    ix->part_scores.release();
+    ix->dbg.release();
+    ix->h_flags.release();
+    ix->h_counts.release();
+    ix->h_slots.release();
+    ix->h_scores.release();
+    ix->h_f32.release();
+    for (cudaEvent_t e : ix->ev) cudaEventDestroy(e);
+    if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
+  }
+  delete ix;
+}
+
+rbk_status rbk_index_set_stream(rbk_index* ix, void* cuda_stream) {
+  if (!ix) return fail(RBK_EINVAL, "null index");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard dg(ix->device);
+  CK(cudaStreamSynchronize(ix->stream));
+  ix->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ix->own_stream;
+  return RBK_OK;
+}
+
+rbk_status rbk_index_set_slot_base(rbk_index* ix, int64_t slot_base) {
+  if (!ix) return fail(RBK_EINVAL, "null index");
+  if (slot_base < 0) return fail(RBK_EINVAL, "slot_base must be >= 0");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  ix->slot_base = slot_base;
+  return RBK_OK;
+}
+
+rbk_status rbk_index_append_f64(rbk_index* ix, const double* rows, int64_t n, int64_t* first) {
+  return append_rows(ix, rows, false, 8, n, first);
+}
+rbk_status rbk_index_append_f32(rbk_index* ix, const float* rows, int64_t n, int64_t* first) {
+  return append_rows(ix, rows, false, 4, n, first);
+}
+rbk_status rbk_index_append_bf16(rbk_index* ix, const uint16_t* rows, int64_t n, int64_t* first) {
+  return append_rows(ix, rows, false, 2, n, first);
+}
+rbk_status rbk_index_append_bf16_device(rbk_index* ix, const void* dev_rows, int64_t n, int64_t* first) {
+  return append_rows(ix, dev_rows, true, 2, n, first);
+}
+
+rbk_status rbk_index_overwrite_f64(rbk_index* ix, int64_t slot, const double* row) {
+  if (!ix || !row) return fail(RBK_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard dg(ix->device);
+  if (slot < 0 || slot >= ix->n_rows) return fail(RBK_EINVAL, "slot out of range");
+  // a tombstoned slot stays dead: the host never overwrites a deleted id (S9b), and the
+  // norm kernel would otherwise revive it
+  unsigned int word = 0;
+  CK(cudaMemcpyAsync(&word, ix->dead_bits + (slot >> 5), 4, cudaMemcpyDeviceToHost, ix->stream));
+  CK(cudaStreamSynchronize(ix->stream));
+  if (word & (1u << (slot & 31))) return fail(RBK_EINVAL, "slot is tombstoned");
+  CK(ix->stage.ensure(static_cast<size_t>(ix->dim) * 8));
+  CK(cudaMemcpyAsync(ix->stage.p, row, static_cast<size_t>(ix->dim) * 8, cudaMemcpyHostToDevice, ix->stream));
+  uint16_t* dst = ix->rows + static_cast<size_t>(slot) * ix->dpad;
+  CK(launch_convert_rows(ix->stage.p, 0, 1, ix->dim, ix->dpad, dst, ix->stream));
+  CK(launch_row_norms(dst, 1, ix->dim, ix->dpad, ix->inv_norm + slot, ix->norm2 + slot, ix->stream));
+  ix->stats.kernel_launches += 2;
+  CK(cudaStreamSynchronize(ix->stream));
+  return RBK_OK;
+}
+
+rbk_status rbk_index_tombstone(rbk_index* ix, const int64_t* slots, int64_t n) {
+  if (!ix) return fail(RBK_EINVAL, "null index");
+  if (n < 0 || (n > 0 && !slots)) return fail(RBK_EINVAL, "bad slots argument");
+  if (n == 0) return RBK_OK;
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard dg(ix->device);
+  for (int64_t i = 0; i < n; ++i)
+    if (slots[i] < 0 || slots[i] >= ix->n_rows) return fail(RBK_EINVAL, "slot out of range");
+  CK(ix->d_slots.ensure(static_cast<size_t>(n)));
+  CK(cudaMemcpyAsync(ix->d_slots.p, slots, sizeof(int64_t) * n, cudaMemcpyHostToDevice, ix->stream));
+  CK(cudaMemsetAsync(ix->d_counter, 0, sizeof(int), ix->stream));
+  CK(launch_tombstone(ix->d_slots.p, n, ix->n_rows, ix->inv_norm, ix->dead_bits, ix->d_counter, ix->stream));
+  ix->stats.kernel_launches++;
+  int killed = 0;
+  CK(cudaMemcpyAsync(&killed, ix->d_counter, sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
+  CK(cudaStreamSynchronize(ix->stream));
+  ix->n_live -= killed;
+  return RBK_OK;
+}
+
+rbk_status rbk_index_clear(rbk_index* ix) {
+  if (!ix) return fail(RBK_EINVAL, "null index");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard dg(ix->device);
+  CK(cudaMemsetAsync(ix->inv_norm, 0xFF, static_cast<size_t>(inv_norm_len(ix->cap)) * 4, ix->stream));
+  CK(cudaMemsetAsync(ix->dead_bits, 0, static_cast<size_t>((ix->cap + 31) / 32) * 4, ix->stream));
+  CK(cudaStreamSynchronize(ix->stream));
+  ix->n_rows = 0;
+  ix->n_live = 0;
+  return RBK_OK;
+}
+
+int64_t rbk_index_count(const rbk_index* ix) { return ix ? ix->n_live : 0; }
+int64_t rbk_index_size(const rbk_index* ix) { return ix ? ix->n_rows : 0; }
+int32_t rbk_index_dim(const rbk_index* ix) { return ix ? ix->dim : 0; }
+
+rbk_status rbk_index_read_rows_bf16(rbk_index* ix, int64_t first, int64_t n, uint16_t* out) {
+  if (!ix || (n > 0 && !out)) return fail(RBK_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard dg(ix->device);
+  if (first < 0 || n < 0 || first + n > ix->n_rows) return fail(RBK_EINVAL, "row range out of bounds");
+  if (n == 0) return RBK_OK;
+  CK(cudaMemcpy2DAsync(out, static_cast<size_t>(ix->dim) * 2, ix->rows + static_cast<size_t>(first) * ix->dpad,
+                       static_cast<size_t>(ix->dpad) * 2, static_cast<size_t>(ix->dim) * 2, static_cast<size_t>(n),
+                       cudaMemcpyDeviceToHost, ix->stream));
+  CK(cudaStreamSynchronize(ix->stream));
+  return RBK_OK;
+}
+
+rbk_status rbk_index_search_f64(rbk_index* ix, const double* queries, int32_t B, int32_t query_dim, int32_t k_fetch,
+                                double min_score, int64_t* out_slots, double* out_scores, int32_t* out_counts,
+                                float* kernel_ms_out) {
+  if (B > 0 && (!out_slots || !out_scores || !out_counts)) return fail(RBK_EINVAL, "null output");
+  return search_core(ix, queries, nullptr, 8, B, query_dim, k_fetch, min_score, nullptr, nullptr, nullptr, out_slots,
+                     out_scores, out_counts, kernel_ms_out);
+}
+rbk_status rbk_index_search_f32(rbk_index* ix, const float* queries, int32_t B, int32_t query_dim, int32_t k_fetch,
+                                double min_score, int64_t* out_slots, double* out_scores, int32_t* out_counts,
+                                float* kernel_ms_out) {
+  if (B > 0 && (!out_slots || !out_scores || !out_counts)) return fail(RBK_EINVAL, "null output");
+  return search_core(ix, queries, nullptr, 4, B, query_dim, k_fetch, min_score, nullptr, nullptr, nullptr, out_slots,
+                     out_scores, out_counts, kernel_ms_out);
+}
+rbk_status rbk_index_search_device(rbk_index* ix, const void* dev_queries_f32, int32_t B, int32_t k_fetch,
+                                   double min_score, void* dev_out_slots, void* dev_out_scores,
+                                   void* dev_out_counts) {
+  if (B > 0 && (!dev_queries_f32 || !dev_out_slots || !dev_out_scores || !dev_out_counts))
+    return fail(RBK_EINVAL, "null device pointer");
+  return search_core(ix, nullptr, dev_queries_f32, 4, B, ix ? ix->dim : 0, k_fetch, min_score,
+                     static_cast<long long*>(dev_out_slots), static_cast<double*>(dev_out_scores),
+                     static_cast<int*>(dev_out_counts), nullptr, nullptr, nullptr, nullptr);
+}
+
+rbk_status rbk_merge_topk_device(int32_t device, void* cuda_stream, int32_t G, int32_t B, int32_t k_fetch,
+                                 const void* dev_slots, const void* dev_scores, const void* dev_counts,
+                                 void* dev_out_slots, void* dev_out_scores, void* dev_out_counts) {
+  if (G < 1 || B < 0 || k_fetch < 1) return fail(RBK_EINVAL, "bad merge shape");
+  if (B == 0) return RBK_OK;
+  if (!dev_slots || !dev_scores || !dev_counts || !dev_out_slots || !dev_out_scores || !dev_out_counts)
+    return fail(RBK_EINVAL, "null device pointer");
+  DeviceGuard dg(device);
+  CK(launch_merge_shards(G, B, k_fetch, static_cast<const long long*>(dev_slots),
+                         static_cast<const double*>(dev_scores), static_cast<const int*>(dev_counts),
+                         static_cast<long long*>(dev_out_slots), static_cast<double*>(dev_out_scores),
+                         static_cast<int*>(dev_out_counts), static_cast<cudaStream_t>(cuda_stream)));
+  return RBK_OK;
+}
+
+rbk_status rbk_index_stats(const rbk_index* ix, rbk_stats* out) {
+  if (!ix || !out) return fail(RBK_EINVAL, "null argument");
+  *out = ix->stats;
+  return RBK_OK;
+}
+
+rbk_status rbk_index_debug_scores_f32(rbk_index* ix, const float* queries, int32_t B, float* out_scores) {
+  if (!ix || !queries || !out_scores || B < 1) return fail(RBK_EINVAL, "bad argument");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard dg(ix->device);
+  if (ix->n_rows == 0) return RBK_OK;
+  rbk_status st = ensure_query_scratch(ix, B, 4);
+  if (st != RBK_OK) return st;
+  const size_t n = static_cast<size_t>(B) * ix->n_rows;
+  CK(ix->dbg.ensure(n));
+  CK(cudaMemsetAsync(ix->dbg.p, 0xFF, n * 4, ix->stream));
+  CK(cudaMemcpyAsync(ix->q_raw.p, queries, static_cast<size_t>(B) * ix->dim * 4, cudaMemcpyHostToDevice, ix->stream));
+  size_t evc = 2;
+  st = run_scan(ix, ix->q_raw.p, 1, B, 16, -INFINITY, nullptr, nullptr, nullptr, ix->dbg.p, &evc);
+  if (st != RBK_OK) return st;
+  std::vector<float> invq(B);
+  CK(cudaMemcpyAsync(out_scores, ix->dbg.p, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+  CK(cudaMemcpyAsync(invq.data(), ix->q_inv_norm.p, sizeof(float) * B, cudaMemcpyDeviceToHost, ix->stream));
+  CK(cudaStreamSynchronize(ix->stream));
+  for (int b = 0; b < B; ++b)
+    for (int64_t r = 0; r < ix->n_rows; ++r) out_scores[static_cast<size_t>(b) * ix->n_rows + r] *= invq[b];
+  return RBK_OK;
+}
+
+}  // extern "C"

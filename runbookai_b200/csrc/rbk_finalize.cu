@@ -1,0 +1,509 @@
+// rbk_finalize.cu — everything around the fused scan that makes the result EXACT:
+//   prep_queries   : per query  bf16 copy for the scan, fp64 copy + exact ||q||^2 (the
+//                    reference's `normA`, embedder.ts:175-180), error bound, start threshold
+//   finalize       : K2 (select the k' best approximate candidates of a query across the
+//                    per-CTA lists) + K4 (re-score them in fp64 in the reference's exact
+//                    operation order, embedder.ts:173-183) + the final ordering of
+//                    VectorStore.search (score desc, stable = slot asc; `>= minScore`;
+//                    vector-store.ts:212,218,221) + the proof that no other row can belong
+//                    to the answer
+//   exact fallback : K0, exhaustive fp64 scan for the (rare) queries whose proof failed
+//   merge_shards   : merge of per-GPU result lists after the all-gather
+#include <cuda_bf16.h>
+#include <limits.h>
+
+#include "rbk_internal.h"
+#include "rbk_ptx.cuh"
+
+namespace rbk {
+
+namespace {
+
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+
+__device__ __forceinline__ double bf16_to_f64(uint32_t h) { return static_cast<double>(__uint_as_float(h << 16)); }
+
+// dot(q, row) accumulated in index order, multiply then add, no FMA (embedder.ts:177-178).
+__device__ __forceinline__ double exact_dot(const double* __restrict__ q, const uint16_t* __restrict__ row, int d) {
+  double dot = 0.0;
+  const uint4* p = reinterpret_cast<const uint4*>(row);
+  int i = 0;
+  for (; i + 8 <= d; i += 8) {
+    const uint4 v = __ldg(p + (i >> 3));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      dot = __dadd_rn(dot, __dmul_rn(__ldg(q + i + 2 * j), bf16_to_f64(w[j] & 0xFFFFu)));
+      dot = __dadd_rn(dot, __dmul_rn(__ldg(q + i + 2 * j + 1), bf16_to_f64(w[j] >> 16)));
+    }
+  }
+  for (; i < d; ++i) dot = __dadd_rn(dot, __dmul_rn(__ldg(q + i), bf16_to_f64(row[i])));
+  return dot;
+}
+// embedder.ts:183  dotProduct / (Math.sqrt(normA) * Math.sqrt(normB))
+__device__ __forceinline__ double exact_cosine(double dot, double na, double nb) {
+  return __ddiv_rn(dot, __dmul_rn(__dsqrt_rn(na), __dsqrt_rn(nb)));
+}
+
+// --------------------------------------------------------------------------- prep
+template <typename SrcT>
+__global__ void __launch_bounds__(128) prep_queries_kernel(const SrcT* __restrict__ src, int d, int dpad,
+                                                           double min_score, double acc_eps, QueryBuffers qb) {
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x;
+  const SrcT* s = src + static_cast<size_t>(q) * d;
+  double sb = 0.0, sd = 0.0;  // ||bf16(q)||^2 and ||q - bf16(q)||^2 (any order: bounds only)
+  for (int i = tid; i < dpad; i += blockDim.x) {
+    uint16_t b = 0;
+    if (i < d) {
+      const double x = static_cast<double>(s[i]);
+      qb.q_f64[static_cast<size_t>(q) * d + i] = x;
+      const __nv_bfloat16 h = __float2bfloat16_rn(__double2float_rn(x));
+      b = __bfloat16_as_ushort(h);
+      const double xb = static_cast<double>(__bfloat162float(h));
+      sb += xb * xb;
+      sd += (x - xb) * (x - xb);
+    }
+    qb.q_bf16[static_cast<size_t>(q) * dpad + i] = b;
+  }
+  __shared__ double red_b[4], red_d[4];
+  __shared__ double s_na;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sb += __shfl_xor_sync(kFull, sb, o);
+    sd += __shfl_xor_sync(kFull, sd, o);
+  }
+  if ((tid & 31) == 0) {
+    red_b[tid >> 5] = sb;
+    red_d[tid >> 5] = sd;
+  }
+  if (tid == 0) {
+    // the reference's normA: index order, multiply then add
+    double na = 0.0;
+    for (int i = 0; i < d; ++i) {
+      const double x = static_cast<double>(s[i]);
+      na = __dadd_rn(na, __dmul_rn(x, x));
+    }
+    s_na = na;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const double na = s_na;
+    const double nb2 = red_b[0] + red_b[1] + red_b[2] + red_b[3];
+    const double nd2 = red_d[0] + red_d[1] + red_d[2] + red_d[3];
+    const bool ok = nb2 > 0.0 && nb2 < INFINITY && na > 0.0 && na < INFINITY;
+    const double inv = ok ? 1.0 / sqrt(nb2) : 0.0;
+    // angle(q, bf16(q)) <= asin(||q - bf16(q)|| / ||q||); cosine is 1-Lipschitz in the angle
+    double ang = 0.0;
+    if (ok && nd2 > 0.0) {
+      const double ratio = sqrt(nd2 / na) * (1.0 + 1e-9);
+      ang = ratio < 1.0 ? asin(ratio) * (1.0 + 1e-9) : 3.2;
+    }
+    const double eps = acc_eps + ang;
+    qb.q_norm2[q] = na;
+    qb.q_eps[q] = eps;
+    const float invf = ok ? static_cast<float>(inv) : __uint_as_float(0x7FC00000u);
+    qb.q_inv_norm[q] = invf;
+    float thr;
+    if (!ok) {
+      thr = INFINITY;  // zero / non-finite query: cosine is NaN for every row (S3) -> nothing matches
+    } else if (min_score == -INFINITY) {
+      thr = -INFINITY;
+    } else {
+      // a row can only reach min_score if approx > min_score - eps; go to the raw domain
+      // (divide by inv_norm_q) and step two ulps down so rounding never hides a row.
+      const double raw = (min_score - eps) / static_cast<double>(invf);
+      float t = static_cast<float>(raw);
+      t = nextafterf(nextafterf(t, -INFINITY), -INFINITY);
+      thr = t;
+    }
+    qb.thr_init[q] = thr;
+  }
+}
+
+// --------------------------------------------------------------------------- finalize
+constexpr int kFinThreads = 256;
+
+// Visit every candidate key of one query: lists (qb, r, qrow) for r in [0, R).
+template <typename F>
+__device__ __forceinline__ void for_each_key(const unsigned long long* __restrict__ cand, const int* s_cnt, int QB, int R,
+                                             int qb, int qrow, F&& f) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < R; r += kFinThreads / 32) {
+    const unsigned long long* l =
+        cand + (static_cast<size_t>(qb * R + r) * kBlockM + qrow) * static_cast<size_t>(kListCap);
+    const int c = s_cnt[r];
+    for (int i = lane; i < c; i += 32) f(__ldcg(l + i));
+  }
+  (void)QB;
+}
+
+__global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p) {
+  const int ql = blockIdx.x;  // query index inside this launch
+  const int tid = threadIdx.x;
+  const int qb = ql / kBlockM, qrow = ql % kBlockM;
+
+  __shared__ int s_cnt[160];
+  __shared__ unsigned int s_hist[256];
+  __shared__ unsigned long long s_sel[kMaxKPrime];
+  __shared__ double s_score[kMaxKPrime];
+  __shared__ int s_row[kMaxKPrime];
+  __shared__ int s_valid[kMaxKPrime];
+  __shared__ int s_total, s_nsel, s_nvalid, s_bin, s_want;
+  __shared__ unsigned long long s_prefix;
+  __shared__ double s_ekth;
+
+  if (tid == 0) {
+    s_total = 0;
+    s_nsel = 0;
+    s_nvalid = 0;
+    s_ekth = 0.0;
+  }
+  __syncthreads();
+  int local = 0;
+  for (int r = tid; r < p.R; r += kFinThreads) {
+    const int c = p.cand_cnt[(qb * p.R + r) * kBlockM + qrow];
+    s_cnt[r] = c;
+    local += c;
+  }
+  if (local) atomicAdd(&s_total, local);
+  __syncthreads();
+  const int M = s_total;
+  const int kprime = p.kprime;
+
+  // ---- K2: radix select of the k'-th largest 64-bit key (keys are unique) ----
+  unsigned long long pivot = 0ull;
+  if (M >= kprime) {
+    if (tid == 0) {
+      s_prefix = 0ull;
+      s_want = kprime;
+    }
+    unsigned long long mask = 0ull;
+    for (int pass = 7; pass >= 0; --pass) {
+      const int shift = pass * 8;
+      s_hist[tid] = 0u;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      for_each_key(p.cand, s_cnt, p.QB, p.R, qb, qrow, [&](unsigned long long k) {
+        if ((k & mask) == prefix) atomicAdd(&s_hist[static_cast<unsigned>(k >> shift) & 255u], 1u);
+      });
+      __syncthreads();
+      if (tid < 32) {
+        // lane L owns bins [255-8L-7, 255-8L]; scan from the top bin down
+        const int top = 255 - 8 * tid;
+        unsigned int mine = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mine += s_hist[top - j];
+        unsigned int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned int v = __shfl_up_sync(kFull, incl, o);
+          if (tid >= o) incl += v;
+        }
+        const unsigned int want = static_cast<unsigned int>(s_want);
+        const bool crosses = (incl >= want) && (incl - mine < want);
+        if (crosses) {
+          unsigned int cum = incl - mine;
+          int b = top;
+          for (int j = 0; j < 8; ++j, --b) {
+            const unsigned int h = s_hist[b];
+            if (cum + h >= want) break;
+            cum += h;
+          }
+          s_bin = b;
+          s_want = static_cast<int>(want - cum);
+        }
+      }
+      __syncthreads();
+      if (tid == 0) s_prefix = prefix | (static_cast<unsigned long long>(s_bin) << shift);
+      mask |= 0xFFull << shift;
+      __syncthreads();
+    }
+    pivot = s_prefix;
+  }
+  for_each_key(p.cand, s_cnt, p.QB, p.R, qb, qrow, [&](unsigned long long k) {
+    if (k >= pivot) {
+      const int pos = atomicAdd(&s_nsel, 1);
+      if (pos < kMaxKPrime) s_sel[pos] = k;
+    }
+  });
+  __syncthreads();
+  const int nsel = s_nsel < kMaxKPrime ? s_nsel : kMaxKPrime;
+  // every row that is NOT a candidate has raw score <= tau_raw (or was cut by thr_init)
+  const float tau_raw = M >= kprime ? key_score(pivot) : -INFINITY;
+
+  // ---- K4: exact fp64 re-score of the candidates ----
+  const double na = p.q.q_norm2[ql];
+  const double* qv = p.q.q_f64 + static_cast<size_t>(ql) * p.d;
+  if (tid < nsel) {
+    const int row = static_cast<int>(key_row(s_sel[tid]));
+    const double dot = exact_dot(qv, p.rows + static_cast<size_t>(row) * p.dpad, p.d);
+    const double sc = exact_cosine(dot, na, p.row_norm2[row]);
+    s_score[tid] = sc;
+    s_row[tid] = row;
+    const int ok = sc >= p.min_score ? 1 : 0;  // vector-store.ts:212 (NaN fails; -inf = no threshold)
+    s_valid[tid] = ok;
+    if (ok) atomicAdd(&s_nvalid, 1);
+  }
+  __syncthreads();
+  const int nvalid = s_nvalid;
+  const int count = nvalid < p.k_fetch ? nvalid : p.k_fetch;
+  // ---- final order: score desc, ties -> lower slot (stable sort over insertion order) ----
+  if (tid < nsel && s_valid[tid]) {
+    const double sc = s_score[tid];
+    const int row = s_row[tid];
+    int rank = 0;
+    for (int j = 0; j < nsel; ++j) {
+      if (!s_valid[j]) continue;
+      const double sj = s_score[j];
+      rank += (sj > sc || (sj == sc && s_row[j] < row)) ? 1 : 0;
+    }
+    if (rank < p.k_fetch) {
+      p.out_slots[static_cast<size_t>(ql) * p.k_fetch + rank] = p.slot_base + row;
+      p.out_scores[static_cast<size_t>(ql) * p.k_fetch + rank] = sc;
+    }
+    if (rank == p.k_fetch - 1) s_ekth = sc;
+  }
+  for (int i = count + tid; i < p.k_fetch; i += kFinThreads) {
+    p.out_slots[static_cast<size_t>(ql) * p.k_fetch + i] = -1;
+    p.out_scores[static_cast<size_t>(ql) * p.k_fetch + i] = __longlong_as_double(0x7FF8000000000000ll);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    p.out_counts[ql] = count;
+    // ---- proof of exactness ----
+    bool ok;
+    if (tau_raw == -INFINITY) {
+      ok = true;  // nothing was ever dropped except by thr_init (provably below min_score)
+    } else {
+      const double bound = static_cast<double>(tau_raw) * static_cast<double>(p.q.q_inv_norm[ql]) + p.q.q_eps[ql];
+      if (count == p.k_fetch) ok = s_ekth > bound;       // every outsider scores strictly below the k-th hit
+      else ok = bound < p.min_score;                      // no outsider can pass the threshold
+    }
+    p.flags[ql] = ok ? 0 : 1;
+  }
+}
+
+// --------------------------------------------------------------------------- exact fallback (K0)
+constexpr int kExThreads = 256;
+constexpr int kExBuf = 1024;
+
+struct ExactTopK {
+  double score[kExBuf];
+  int row[kExBuf];
+  int n;
+  int have_thr;
+  double thr_score;
+  int thr_row;
+};
+
+__device__ __forceinline__ bool hit_before(double sa, int ra, double sb, int rb) {
+  return sa > sb || (sa == sb && ra < rb);
+}
+
+// Block-wide: sort the buffer by (score desc, row asc), keep the best K.
+__device__ void exact_compact(ExactTopK& t, int K) {
+  const int tid = threadIdx.x;
+  __syncthreads();
+  const int n = t.n;
+  for (int i = n + tid; i < kExBuf; i += kExThreads) {
+    t.score[i] = -INFINITY;
+    t.row[i] = INT_MAX;
+  }
+  __syncthreads();
+  for (int k2 = 2; k2 <= kExBuf; k2 <<= 1) {
+    for (int s = k2 >> 1; s > 0; s >>= 1) {
+      for (int i = tid; i < kExBuf; i += kExThreads) {
+        const int j = i ^ s;
+        if (j > i) {
+          const bool desc = (i & k2) == 0;
+          const bool j_first = hit_before(t.score[j], t.row[j], t.score[i], t.row[i]);
+          if (desc ? j_first : !j_first) {
+            const double ts = t.score[i];
+            t.score[i] = t.score[j];
+            t.score[j] = ts;
+            const int tr = t.row[i];
+            t.row[i] = t.row[j];
+            t.row[j] = tr;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (tid == 0) {
+    const int keep = n < K ? n : K;
+    t.n = keep;
+    if (keep == K) {
+      t.have_thr = 1;
+      t.thr_score = t.score[K - 1];
+      t.thr_row = t.row[K - 1];
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void exact_push(ExactTopK& t, double sc, int row) {
+  if (t.have_thr && !hit_before(sc, row, t.thr_score, t.thr_row)) return;
+  const int pos = atomicAdd(&t.n, 1);
+  t.score[pos] = sc;
+  t.row[pos] = row;
+}
+
+__global__ void __launch_bounds__(kExThreads) exact_scan_kernel(ExactParams p) {
+  __shared__ ExactTopK t;
+  const int tid = threadIdx.x;
+  const int f = blockIdx.y;
+  const int q = p.fail_list[f];
+  if (tid == 0) {
+    t.n = 0;
+    t.have_thr = 0;
+  }
+  __syncthreads();
+  const int64_t chunk = (p.n_rows + p.n_blocks - 1) / p.n_blocks;
+  const int64_t r0 = blockIdx.x * chunk;
+  const int64_t r1 = r0 + chunk < p.n_rows ? r0 + chunk : p.n_rows;
+  const double* qv = p.q_f64 + static_cast<size_t>(q) * p.d;
+  const double na = p.q_norm2[q];
+  for (int64_t base = r0; base < r1; base += kExThreads) {
+    if (t.n > kExBuf - kExThreads) exact_compact(t, p.k_fetch);  // uniform: t.n read after a barrier
+    const int64_t row = base + tid;
+    if (row < r1) {
+      const float ic = p.inv_norm_c[row];
+      if (ic == ic) {  // live, non-zero row
+        const double dot = exact_dot(qv, p.rows + static_cast<size_t>(row) * p.dpad, p.d);
+        const double sc = exact_cosine(dot, na, p.row_norm2[row]);
+        if (sc >= p.min_score) exact_push(t, sc, static_cast<int>(row));
+      }
+    }
+    __syncthreads();
+  }
+  exact_compact(t, p.k_fetch);
+  const size_t o = (static_cast<size_t>(f) * p.n_blocks + blockIdx.x) * p.k_fetch;
+  for (int i = tid; i < t.n; i += kExThreads) {
+    p.part_scores[o + i] = t.score[i];
+    p.part_rows[o + i] = t.row[i];
+  }
+  if (tid == 0) p.part_cnt[f * p.n_blocks + blockIdx.x] = t.n;
+}
+
+__global__ void __launch_bounds__(kExThreads) exact_merge_kernel(ExactParams p) {
+  __shared__ ExactTopK t;
+  const int tid = threadIdx.x;
+  const int f = blockIdx.x;
+  const int q = p.fail_list[f];
+  if (tid == 0) {
+    t.n = 0;
+    t.have_thr = 0;
+  }
+  __syncthreads();
+  const int total = p.n_blocks * p.k_fetch;
+  for (int base = 0; base < total; base += kExThreads) {
+    if (t.n > kExBuf - kExThreads) exact_compact(t, p.k_fetch);
+    const int i = base + tid;
+    if (i < total) {
+      const int b = i / p.k_fetch, e = i % p.k_fetch;
+      if (e < p.part_cnt[f * p.n_blocks + b]) {
+        const size_t o = (static_cast<size_t>(f) * p.n_blocks + b) * p.k_fetch + e;
+        exact_push(t, p.part_scores[o], p.part_rows[o]);
+      }
+    }
+    __syncthreads();
+  }
+  exact_compact(t, p.k_fetch);
+  const int n = t.n;
+  for (int i = tid; i < p.k_fetch; i += kExThreads) {
+    const size_t o = static_cast<size_t>(q) * p.k_fetch + i;
+    if (i < n) {
+      p.out_slots[o] = p.slot_base + t.row[i];
+      p.out_scores[o] = t.score[i];
+    } else {
+      p.out_slots[o] = -1;
+      p.out_scores[o] = __longlong_as_double(0x7FF8000000000000ll);
+    }
+  }
+  if (tid == 0) p.out_counts[q] = n;
+}
+
+// --------------------------------------------------------------------------- shard merge
+// Lists are sorted by (score desc, slot asc); slots are globally unique, so the rank of an
+// entry in the merged order is its own index plus, for every other list, the number of
+// entries of that list that come before it (binary search).
+__global__ void __launch_bounds__(128) merge_shards_kernel(int G, int B, int k, const long long* __restrict__ slots,
+                                                           const double* __restrict__ scores,
+                                                           const int* __restrict__ counts, long long* out_slots,
+                                                           double* out_scores, int* out_counts) {
+  const int b = blockIdx.x;
+  int total = 0;
+  for (int g = 0; g < G; ++g) total += counts[g * B + b];
+  const int n_out = total < k ? total : k;
+  for (int i = threadIdx.x; i < G * k; i += blockDim.x) {
+    const int g = i / k, e = i % k;
+    if (e >= counts[g * B + b]) continue;
+    const size_t o = (static_cast<size_t>(g) * B + b) * k;
+    const double sc = scores[o + e];
+    const long long sl = slots[o + e];
+    int rank = e;
+    for (int g2 = 0; g2 < G; ++g2) {
+      if (g2 == g) continue;
+      const size_t o2 = (static_cast<size_t>(g2) * B + b) * k;
+      int lo = 0, hi = counts[g2 * B + b];
+      while (lo < hi) {  // first index whose entry does NOT come before (sc, sl)
+        const int mid = (lo + hi) >> 1;
+        const double s2 = scores[o2 + mid];
+        const long long l2 = slots[o2 + mid];
+        if (s2 > sc || (s2 == sc && l2 < sl)) lo = mid + 1;
+        else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank < k) {
+      out_slots[static_cast<size_t>(b) * k + rank] = sl;
+      out_scores[static_cast<size_t>(b) * k + rank] = sc;
+    }
+  }
+  for (int i = n_out + threadIdx.x; i < k; i += blockDim.x) {
+    out_slots[static_cast<size_t>(b) * k + i] = -1;
+    out_scores[static_cast<size_t>(b) * k + i] = __longlong_as_double(0x7FF8000000000000ll);
+  }
+  if (threadIdx.x == 0) out_counts[b] = n_out;
+}
+
+}  // namespace
+
+cudaError_t launch_prep_queries(const void* src, int src_type, int B, int d, int dpad, double min_score,
+                                const QueryBuffers& qb, cudaStream_t stream) {
+  if (B <= 0) return cudaSuccess;
+  const double acc_eps = accumulation_eps(d);
+  if (src_type == 0)
+    prep_queries_kernel<double><<<B, 128, 0, stream>>>(static_cast<const double*>(src), d, dpad, min_score, acc_eps, qb);
+  else
+    prep_queries_kernel<float><<<B, 128, 0, stream>>>(static_cast<const float*>(src), d, dpad, min_score, acc_eps, qb);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t stream) {
+  if (p.B <= 0) return cudaSuccess;
+  finalize_kernel<<<p.B, kFinThreads, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_exact_fallback(const ExactParams& p, cudaStream_t stream) {
+  if (p.n_fail <= 0) return cudaSuccess;
+  dim3 grid(p.n_blocks, p.n_fail);
+  exact_scan_kernel<<<grid, kExThreads, 0, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  exact_merge_kernel<<<p.n_fail, kExThreads, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_merge_shards(int G, int B, int k_fetch, const long long* slots, const double* scores,
+                                const int* counts, long long* out_slots, double* out_scores, int* out_counts,
+                                cudaStream_t stream) {
+  if (B <= 0) return cudaSuccess;
+  merge_shards_kernel<<<B, 128, 0, stream>>>(G, B, k_fetch, slots, scores, counts, out_slots, out_scores, out_counts);
+  return cudaGetLastError();
+}
+
+}  // namespace rbk

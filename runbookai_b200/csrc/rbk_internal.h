@@ -1,0 +1,107 @@
+// rbk_internal.h — declarations shared by the kernels and the C-ABI translation unit.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rbk {
+
+// ---- tiling of the fused scan (rbk_scan.cu) ----
+constexpr int kBlockM = 128;      // queries per CTA (UMMA M, TMEM lanes)
+constexpr int kBlockN = 256;      // corpus rows per tile (UMMA N, TMEM columns)
+constexpr int kBlockK = 64;       // bf16 elements per pipeline stage (one 128-byte swizzle row)
+constexpr int kStages = 4;        // smem ring depth
+constexpr int kListCap = 256;     // entries per (CTA, query) candidate list
+constexpr int kMaxKPrime = 128;   // candidates kept per query (k_fetch + margin)
+constexpr int kScanThreads = 192; // warp0 TMA, warp1 MMA/TMEM, warps2-5 epilogue
+constexpr int kMaxSubBatch = 1024;  // queries per scan launch (8 query blocks)
+
+struct ScanParams {
+  const float* inv_norm_c;  // [rows padded to kBlockN], NaN = dead / out of range
+  const float* thr_init;    // [B] initial threshold, raw domain (acc * inv_norm_c); -inf = none
+  unsigned long long* cand; // [QB][R][kBlockM][kListCap] packed keys
+  int* cand_cnt;            // [QB][R][kBlockM]
+  float* dbg_scores;        // nullable: [B][n_rows] raw-domain scores (validation aid)
+  int n_rows;
+  int B;        // queries in this launch
+  int kprime;
+  int num_kb;   // k-blocks per tile = ceil(dpad / kBlockK)
+  int QB;       // query blocks
+  int R;        // corpus ranges (CTAs per query block)
+  int n_tiles;  // ceil(n_rows / kBlockN)
+};
+
+cudaError_t launch_scan(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const ScanParams& p,
+                        cudaStream_t stream);
+size_t scan_smem_bytes();
+
+// ---- ingest (rbk_ingest.cu) ----
+// src element type: 0 = f64, 1 = f32, 2 = bf16 bits.  src is device memory, row pitch = d.
+cudaError_t launch_convert_rows(const void* src, int src_type, int64_t n_rows, int d, int dpad,
+                                uint16_t* dst_rows, cudaStream_t stream);
+cudaError_t launch_row_norms(const uint16_t* rows, int64_t n_rows, int d, int dpad, float* inv_norm,
+                             double* norm2, cudaStream_t stream);
+cudaError_t launch_tombstone(const int64_t* dev_slots, int64_t n, int64_t n_rows, float* inv_norm,
+                             unsigned int* dead_bits, int* n_killed, cudaStream_t stream);
+
+// ---- query preparation + finalize + exhaustive fallback + shard merge (rbk_finalize.cu) ----
+struct QueryBuffers {
+  uint16_t* q_bf16;    // [B][dpad]
+  double* q_f64;       // [B][d]
+  double* q_norm2;     // [B] exact sequential sum of squares of the f64 query (reference's normA)
+  float* q_inv_norm;   // [B] 1/||bf16(q)||  (approximate-score scaling)
+  double* q_eps;       // [B] bound on |approx - exact| cosine for this query
+  float* thr_init;     // [B]
+};
+// src_type: 0 = f64, 1 = f32 (device pointers, row pitch d)
+cudaError_t launch_prep_queries(const void* src, int src_type, int B, int d, int dpad, double min_score,
+                                const QueryBuffers& qb, cudaStream_t stream);
+
+struct FinalizeParams {
+  const unsigned long long* cand;
+  const int* cand_cnt;
+  int QB, R, kprime, k_fetch, B, d, dpad;
+  int q0;  // global index of the first query of this launch (sub-batch offset)
+  double min_score;
+  const uint16_t* rows;
+  const double* row_norm2;
+  int64_t n_rows;
+  int64_t slot_base;
+  QueryBuffers q;  // pointers already offset to the sub-batch
+  long long* out_slots;   // [B][k_fetch]
+  double* out_scores;     // [B][k_fetch]
+  int* out_counts;        // [B]
+  int* flags;             // [B] 1 = not provably exact -> exhaustive fallback
+};
+cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t stream);
+
+struct ExactParams {
+  const int* fail_list;  // [n_fail] query indices
+  int n_fail;
+  int d, dpad, k_fetch;
+  double min_score;
+  const uint16_t* rows;
+  const double* row_norm2;
+  const float* inv_norm_c;  // NaN marks dead rows
+  int64_t n_rows;
+  int64_t slot_base;
+  const double* q_f64;
+  const double* q_norm2;
+  double* part_scores;   // [n_fail][n_blocks][k_fetch]
+  int* part_rows;        // [n_fail][n_blocks][k_fetch]
+  int* part_cnt;         // [n_fail][n_blocks]
+  int n_blocks;
+  long long* out_slots;
+  double* out_scores;
+  int* out_counts;
+};
+cudaError_t launch_exact_fallback(const ExactParams& p, cudaStream_t stream);
+
+cudaError_t launch_merge_shards(int G, int B, int k_fetch, const long long* slots, const double* scores,
+                                const int* counts, long long* out_slots, double* out_scores, int* out_counts,
+                                cudaStream_t stream);
+
+// Bound on the fp32 tensor-core accumulation + scaling error of an approximate cosine.
+inline double accumulation_eps(int d) { return (double)(d + 8) * (1.0 / 4194304.0); }  // (d+8) * 2^-22
+
+}  // namespace rbk

@@ -1,0 +1,295 @@
+// rbk_scan.cu — K1: fused  Q x C^T (tcgen05, bf16 -> fp32 in TMEM)  +  row-norm scaling
+//               +  per-query running top-k' selection in the epilogue.
+//
+// Replaces the hot loop of VectorStore.search (reference src/knowledge/store/
+// vector-store.ts:207-215 calling cosineSimilarity, src/knowledge/indexer/
+// embedder.ts:168-184) for a whole batch of queries at once.  The score matrix never
+// reaches HBM: each epilogue thread owns one query (one TMEM lane), streams the 256
+// scores of a tile out of TMEM, compares them with that query's running threshold and
+// appends the rare survivors to a small per-(CTA, query) candidate list.
+//
+// Work decomposition (persistent CTAs, one per SM):
+//   CTA c -> query block qb = c % QB (128 queries), corpus range r = c / QB.
+//   CTAs that share r walk the same corpus tiles at the same pace, so a tile is pulled
+//   from HBM once and served to the other query blocks from L2.
+// Warp roles: warp 0 = TMA producer (1 thread), warp 1 = TMEM owner + MMA issuer
+//   (1 thread), warps 2..5 = epilogue (TMEM lane quadrant = warp % 4).
+// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM double buffer full/empty
+//   (MMA <-> epilogue): the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "rbk_internal.h"
+#include "rbk_ptx.cuh"
+
+namespace rbk {
+
+namespace {
+
+constexpr int kABytes = kBlockM * kBlockK * 2;      // 16 KiB  query k-slab
+constexpr int kBBytes = kBlockN * kBlockK * 2;      // 32 KiB  corpus k-slab
+constexpr int kStageBytes = kABytes + kBBytes;      // 48 KiB
+constexpr int kTmemCols = 512;                      // 2 accumulator stages x 256 fp32 columns
+constexpr int kEpiThreads = 128;
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+
+struct SmemTail {
+  float invc[2][kBlockN];  // 1/||c|| of the tile's rows, per accumulator stage
+  unsigned long long full[kStages];
+  unsigned long long empty[kStages];
+  unsigned long long tmem_full[2];
+  unsigned long long tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) {
+  return a > b ? a : b;
+}
+__device__ __forceinline__ unsigned long long umin64(unsigned long long a, unsigned long long b) {
+  return a < b ? a : b;
+}
+
+// Warp-cooperative compaction of one query's candidate list: bitonic sort of up to 256
+// keys (8 per lane, element i = j*32 + lane), keep the best k', return the k'-th score.
+__device__ __noinline__ void warp_compact(unsigned long long* list, int cnt, int kprime, int lane, float& new_thr,
+                                          int& new_cnt) {
+  unsigned long long k[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int idx = j * 32 + lane;
+    k[j] = idx < cnt ? __ldcg(list + idx) : 0ull;
+  }
+#pragma unroll
+  for (int k2 = 2; k2 <= 256; k2 <<= 1) {
+#pragma unroll
+    for (int s = k2 >> 1; s > 0; s >>= 1) {
+      if (s >= 32) {
+        const int js = s >> 5;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if ((j & js) == 0) {
+            const int i = j * 32 + lane;
+            const bool desc = (i & k2) == 0;
+            const unsigned long long a = k[j], b = k[j | js];
+            const unsigned long long hi = umax64(a, b), lo = umin64(a, b);
+            k[j] = desc ? hi : lo;
+            k[j | js] = desc ? lo : hi;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int i = j * 32 + lane;
+          const unsigned long long other = __shfl_xor_sync(kFull, k[j], s);
+          const bool lower = (lane & s) == 0;
+          const bool desc = (i & k2) == 0;
+          k[j] = (lower == desc) ? umax64(k[j], other) : umin64(k[j], other);
+        }
+      }
+    }
+  }
+  const int keep = cnt < kprime ? cnt : kprime;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int idx = j * 32 + lane;
+    if (idx < keep) list[idx] = k[j];
+  }
+  const int e = kprime - 1;
+  unsigned long long sel = 0ull;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j == (e >> 5)) sel = k[j];
+  const unsigned long long kth = __shfl_sync(kFull, sel, e & 31);
+  new_thr = cnt >= kprime ? key_score(kth) : -INFINITY;
+  new_cnt = keep;
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kScanThreads, 1)
+scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
+            const ScanParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B needs 1024-B alignment
+  SmemTail* tail = reinterpret_cast<SmemTail*>(smem + kStages * kStageBytes);
+  const uint32_t smem_base = smem_u32(smem);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qb = blockIdx.x % p.QB;
+  const int r = blockIdx.x / p.QB;
+  const int t0 = static_cast<int>(static_cast<long long>(p.n_tiles) * r / p.R);
+  const int t1 = static_cast<int>(static_cast<long long>(p.n_tiles) * (r + 1) / p.R);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_c);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(&tail->full[s]), 1);
+      mbar_init(smem_u32(&tail->empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tail->tmem_full[a]), 1);
+      mbar_init(smem_u32(&tail->tmem_empty[a]), 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tail->tmem_base), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one thread) =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = t0; tile < t1; ++tile) {
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
+          const uint32_t full = smem_u32(&tail->full[s]);
+          mbar_arrive_expect_tx(full, kStageBytes);
+          const uint32_t a_dst = smem_base + s * kStageBytes;
+          tma_load_2d(a_dst, &tmap_q, full, kb * kBlockK, qb * kBlockM);
+          tma_load_2d(a_dst + kABytes, &tmap_c, full, kb * kBlockK, tile * kBlockN);
+          if (++s == kStages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(kBlockM, kBlockN);
+      int s = 0, as = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int tile = t0; tile < t1; ++tile) {
+        mbar_wait(smem_u32(&tail->tmem_empty[as]), aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * kBlockN);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(smem_u32(&tail->full[s]), ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_base + s * kStageBytes;
+          const uint32_t b0 = a0 + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            umma_bf16_ss(d_tmem, make_sw128_kmajor_desc(a0 + k * 32), make_sw128_kmajor_desc(b0 + k * 32), idesc,
+                         (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&tail->empty[s]));  // smem slot reusable once these MMAs retire
+          if (kb == p.num_kb - 1) umma_commit(smem_u32(&tail->tmem_full[as]));
+          if (++s == kStages) { s = 0; ph ^= 1u; }
+        }
+        as ^= 1;
+        if (as == 0) aph ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue: thread <-> query =====================
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may read
+    const int qrow = quad * 32 + lane;    // row of the 128-query block == TMEM lane
+    const int q = qb * kBlockM + qrow;
+    const bool q_valid = q < p.B;
+    const int et = threadIdx.x - 64;      // 0..127
+    float thr = q_valid ? p.thr_init[q] : INFINITY;
+    int cnt = 0;
+    unsigned long long* list =
+        p.cand + (static_cast<size_t>(qb * p.R + r) * kBlockM + qrow) * static_cast<size_t>(kListCap);
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = t0; tile < t1; ++tile) {
+      const int row0 = tile * kBlockN;
+      const float ic0 = __ldg(p.inv_norm_c + row0 + et);
+      const float ic1 = __ldg(p.inv_norm_c + row0 + kEpiThreads + et);
+      tail->invc[as][et] = ic0;
+      tail->invc[as][kEpiThreads + et] = ic1;
+      named_bar_sync(1, kEpiThreads);
+      mbar_wait(smem_u32(&tail->tmem_full[as]), aph);
+      tc_fence_after();
+      const float* invc = tail->invc[as];
+#pragma unroll 1
+      for (int chunk = 0; chunk < kBlockN / 32; ++chunk) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                               static_cast<uint32_t>(as * kBlockN + chunk * 32),
+                           v);
+        tmem_wait_ld();
+        const float4* ic4 = reinterpret_cast<const float4*>(invc + chunk * 32);
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 w = ic4[j];
+          const float a0 = __uint_as_float(v[4 * j + 0]) * w.x;
+          const float a1 = __uint_as_float(v[4 * j + 1]) * w.y;
+          const float a2 = __uint_as_float(v[4 * j + 2]) * w.z;
+          const float a3 = __uint_as_float(v[4 * j + 3]) * w.w;
+          m = fmaxf(m, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));  // fmaxf drops NaN (dead rows)
+        }
+        if (m > thr) {  // rare: at least one survivor in this chunk for this query
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float t = __uint_as_float(v[j]) * invc[chunk * 32 + j];
+            if (t > thr) {
+              list[cnt] = pack_key(t, static_cast<uint32_t>(row0 + chunk * 32 + j));
+              ++cnt;
+            }
+          }
+        }
+        if (p.dbg_scores != nullptr && q_valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int row = row0 + chunk * 32 + j;
+            if (row < p.n_rows)
+              p.dbg_scores[static_cast<size_t>(q) * p.n_rows + row] = __uint_as_float(v[j]) * invc[chunk * 32 + j];
+          }
+        }
+        __syncwarp();
+        unsigned need = __ballot_sync(kFull, cnt > kListCap - 32);
+        while (need) {
+          const int src = __ffs(need) - 1;
+          need &= need - 1;
+          unsigned long long* l =
+              reinterpret_cast<unsigned long long*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(list), src));
+          const int c = __shfl_sync(kFull, cnt, src);
+          float nt;
+          int nc;
+          warp_compact(l, c, p.kprime, lane, nt, nc);
+          if (lane == src) {
+            thr = fmaxf(thr, nt);
+            cnt = nc;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tail->tmem_empty[as]));
+      as ^= 1;
+      if (as == 0) aph ^= 1u;
+    }
+    p.cand_cnt[(qb * p.R + r) * kBlockM + qrow] = cnt;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+size_t scan_smem_bytes() { return static_cast<size_t>(kStages) * kStageBytes + sizeof(SmemTail) + 1024; }
+
+cudaError_t launch_scan(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const ScanParams& p,
+                        cudaStream_t stream) {
+  const size_t smem = scan_smem_bytes();
+  // per-device attribute; cheap enough to set on every launch
+  cudaError_t e = cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  scan_kernel<<<p.QB * p.R, kScanThreads, smem, stream>>>(tmap_q, tmap_c, p);
+  return cudaGetLastError();
+}
+
+}  // namespace rbk
