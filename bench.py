@@ -205,13 +205,14 @@ def main():
         torch.cuda.synchronize(device)
 
     # ---------------- value: batch resident in HBM ----------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # nvidia-smi needs a moment to start: launch it before the warm-up
     for _ in range(args.warmup):
         searcher.search_device(q_dev, k_fetch, None)
     launches0 = ix.stats()["kernel_launches"]
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     barrier()
+    sampler.rows.clear()         # keep only samples taken inside the timed region
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scan_ms = []
     ev0.record(stream)

@@ -135,7 +135,8 @@ struct rbk_index {
   DevBuf<double> q_f64, q_norm2, q_eps;
   DevBuf<float> q_inv_norm, thr_init;
   DevBuf<unsigned long long> cand;
-  DevBuf<int> cand_cnt, flags, fail_list, o_counts, part_rows, part_cnt;
+  DevBuf<int> cand_cnt, flags, fail_list, o_counts, part_rows, part_cnt, maxbin, progress;
+  DevBuf<unsigned int> hist;
   DevBuf<long long> o_slots;
   DevBuf<double> o_scores, part_scores;
   DevBuf<float> dbg;
@@ -284,6 +285,9 @@ rbk_status ensure_query_scratch(rbk_index* ix, int B, int elem) {
   CK(ix->flags.ensure(B));
   CK(ix->cand.ensure(static_cast<size_t>(ix->sm_count) * kBlockM * kListCap));
   CK(ix->cand_cnt.ensure(static_cast<size_t>(ix->sm_count) * kBlockM));
+  CK(ix->hist.ensure(static_cast<size_t>(kMaxSubBatch) * kHistBins));
+  CK(ix->maxbin.ensure(kMaxSubBatch));
+  CK(ix->progress.ensure(static_cast<size_t>(ix->sm_count) + 8));
   return RBK_OK;
 }
 
@@ -328,6 +332,13 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
     ScanParams sp;
     sp.inv_norm_c = ix->inv_norm;
     sp.thr_init = ix->thr_init.p + q0;
+    sp.inv_norm_q = ix->q_inv_norm.p + q0;
+    sp.hist = ix->hist.p;
+    sp.maxbin = ix->maxbin.p;
+    sp.progress = ix->progress.p;
+    CK(cudaMemsetAsync(ix->progress.p, 0, sizeof(int) * (static_cast<size_t>(ix->sm_count) + 8), ix->stream));
+    CK(cudaMemsetAsync(ix->hist.p, 0, sizeof(unsigned int) * static_cast<size_t>(Bs) * kHistBins, ix->stream));
+    CK(cudaMemsetAsync(ix->maxbin.p, 0, sizeof(int) * Bs, ix->stream));
     sp.cand = ix->cand.p;
     sp.cand_cnt = ix->cand_cnt.p;
     sp.dbg_scores = dbg ? dbg + static_cast<size_t>(q0) * ix->n_rows : nullptr;
@@ -565,6 +576,9 @@ void rbk_index_destroy(rbk_index* ix) {
     ix->thr_init.release();
     ix->cand.release();
     ix->cand_cnt.release();
+    ix->hist.release();
+    ix->maxbin.release();
+    ix->progress.release();
     ix->flags.release();
     ix->fail_list.release();
     ix->o_counts.release();

@@ -1,0 +1,208 @@
+// rbk_epilogue.cuh — per-query candidate filter shared by the scan kernels' epilogues.
+//
+// One epilogue thread owns one query.  It keeps a running threshold `thr` (raw domain:
+// accumulator * 1/||c||) and appends the rare survivors to its (CTA, query) list.  The
+// threshold comes from three sources, all of them LOWER bounds on the query's global k'-th
+// best score, so dropping a row at or below it is always safe:
+//   1. min_score - eps (prep kernel),
+//   2. the k'-th best of the thread's own list after a compaction,
+//   3. a global per-query histogram of the scores of ALL appended rows (every CTA adds to
+//      it): the highest bin edge with >= k' rows at or above it.  This is what makes the
+//      threshold track the true running k'-th best of the whole corpus instead of one
+//      CTA's slice, so after the first few chunks almost nothing is appended any more.
+#pragma once
+#include "rbk_internal.h"
+#include "rbk_ptx.cuh"
+
+namespace rbk {
+
+struct FilterState {
+  float thr;       // raw-domain threshold
+  float inv_q;     // 1/||bf16(q)||: raw -> approximate cosine
+  float qn;        // ||bf16(q)||
+  int tb;          // histogram bin whose lower edge produced thr (-1: none yet)
+  int mb_cache;    // highest bin this thread already published to maxbin
+  int cnt;         // entries in the list
+  bool valid;
+  unsigned long long* list;
+  unsigned int* hist_q;  // [kHistBins]
+  int* maxbin_q;
+};
+
+__device__ __forceinline__ int score_bin(float a) {
+  const int b = static_cast<int>((a + 1.0f) * (kHistBins * 0.5f));
+  return min(max(b, 0), kHistBins - 1);
+}
+// Raw threshold such that every row counted in bins >= b has raw score > the result.
+__device__ __forceinline__ float bin_edge_raw(int b, float qn) {
+  const float edge = static_cast<float>(b) * (2.0f / kHistBins) - 1.0f - 1e-6f;  // cosine domain, nudged down
+  const float r = edge * qn;
+  return r - fabsf(r) * 1e-6f;
+}
+
+__device__ __forceinline__ void filter_init(FilterState& s, bool valid, float thr_init, float inv_q,
+                                            unsigned long long* list, unsigned int* hist_q, int* maxbin_q) {
+  s.valid = valid && thr_init < INFINITY;
+  s.thr = s.valid ? thr_init : INFINITY;
+  s.inv_q = s.valid ? inv_q : 0.f;
+  s.qn = s.valid ? 1.0f / inv_q : 0.f;
+  s.tb = (s.valid && thr_init > -INFINITY) ? score_bin(thr_init * inv_q) : -1;
+  s.mb_cache = -1;
+  s.cnt = 0;
+  s.list = list;
+  s.hist_q = hist_q;
+  s.maxbin_q = maxbin_q;
+}
+
+// Raise thr from the global histogram (source 3).  Per-thread, no warp collectives.
+__device__ __noinline__ void filter_refresh(FilterState& s, int kprime) {
+  if (!s.valid) return;
+  const int mb = __ldcg(s.maxbin_q);
+  if (mb <= s.tb) return;
+  const uint4* h4 = reinterpret_cast<const uint4*>(s.hist_q);
+  const int g_lo = (s.tb + 1) >> 2;
+  int g = mb >> 2;
+  unsigned cum = 0;
+  uint4 cur = __ldcg(h4 + g);
+  while (true) {
+    uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+    if (g > g_lo) nxt = __ldcg(h4 + g - 1);
+    const unsigned c[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+    for (int j = 3; j >= 0; --j) {
+      const int b = g * 4 + j;
+      if (b <= mb && b > s.tb) {
+        cum += c[j];
+        if (cum >= static_cast<unsigned>(kprime)) {
+          s.tb = b;
+          s.thr = fmaxf(s.thr, bin_edge_raw(b, s.qn));
+          return;
+        }
+      }
+    }
+    if (g <= g_lo) return;
+    --g;
+    cur = nxt;
+  }
+}
+
+__device__ __forceinline__ void filter_append(FilterState& s, float t, uint32_t row) {
+  s.list[s.cnt] = pack_key(t, row);
+  ++s.cnt;
+  const int b = score_bin(t * s.inv_q);
+  atomicAdd(s.hist_q + b, 1u);
+  if (b > s.mb_cache) {
+    atomicMax(s.maxbin_q, b);
+    s.mb_cache = b;
+  }
+}
+
+// 32 accumulator columns of this thread's query; invc32 = the 32 matching 1/||c|| (smem).
+__device__ __forceinline__ void filter_chunk(FilterState& s, const uint32_t (&v)[32], const float* invc32,
+                                             uint32_t row_base) {
+  const float4* ic4 = reinterpret_cast<const float4*>(invc32);
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 w = ic4[j];
+    const float a0 = __uint_as_float(v[4 * j + 0]) * w.x;
+    const float a1 = __uint_as_float(v[4 * j + 1]) * w.y;
+    const float a2 = __uint_as_float(v[4 * j + 2]) * w.z;
+    const float a3 = __uint_as_float(v[4 * j + 3]) * w.w;
+    m = fmaxf(m, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));  // fmaxf drops NaN (dead / out-of-range rows)
+  }
+  if (m > s.thr) {  // rare once the threshold has converged
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float t = __uint_as_float(v[j]) * invc32[j];
+      if (t > s.thr) filter_append(s, t, row_base + j);
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) {
+  return a > b ? a : b;
+}
+__device__ __forceinline__ unsigned long long umin64(unsigned long long a, unsigned long long b) {
+  return a < b ? a : b;
+}
+
+// Warp-cooperative compaction of one list: bitonic sort of up to 256 keys (8 per lane,
+// element i = j*32 + lane), keep the best k', return the k'-th score (source 2).
+__device__ __noinline__ void warp_compact(unsigned long long* list, int cnt, int kprime, int lane, float& new_thr,
+                                          int& new_cnt) {
+  constexpr uint32_t kFullMask = 0xFFFFFFFFu;
+  unsigned long long k[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int idx = j * 32 + lane;
+    k[j] = idx < cnt ? __ldcg(list + idx) : 0ull;
+  }
+#pragma unroll
+  for (int k2 = 2; k2 <= 256; k2 <<= 1) {
+#pragma unroll
+    for (int st = k2 >> 1; st > 0; st >>= 1) {
+      if (st >= 32) {
+        const int js = st >> 5;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if ((j & js) == 0) {
+            const int i = j * 32 + lane;
+            const bool desc = (i & k2) == 0;
+            const unsigned long long a = k[j], b = k[j | js];
+            const unsigned long long hi = umax64(a, b), lo = umin64(a, b);
+            k[j] = desc ? hi : lo;
+            k[j | js] = desc ? lo : hi;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int i = j * 32 + lane;
+          const unsigned long long other = __shfl_xor_sync(kFullMask, k[j], st);
+          const bool lower = (lane & st) == 0;
+          const bool desc = (i & k2) == 0;
+          k[j] = (lower == desc) ? umax64(k[j], other) : umin64(k[j], other);
+        }
+      }
+    }
+  }
+  const int keep = cnt < kprime ? cnt : kprime;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int idx = j * 32 + lane;
+    if (idx < keep) list[idx] = k[j];
+  }
+  const int e = kprime - 1;
+  unsigned long long sel = 0ull;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j == (e >> 5)) sel = k[j];
+  const unsigned long long kth = __shfl_sync(kFullMask, sel, e & 31);
+  new_thr = cnt >= kprime ? key_score(kth) : -INFINITY;
+  new_cnt = keep;
+  __syncwarp();
+}
+
+// Warp-collective: compact every lane's list that could overflow on the next chunk.
+__device__ __forceinline__ void filter_compact_if_needed(FilterState& s, int kprime, int lane) {
+  constexpr uint32_t kFullMask = 0xFFFFFFFFu;
+  __syncwarp();
+  unsigned need = __ballot_sync(kFullMask, s.cnt > kListCap - 32);
+  while (need) {
+    const int src = __ffs(need) - 1;
+    need &= need - 1;
+    unsigned long long* l = reinterpret_cast<unsigned long long*>(
+        __shfl_sync(kFullMask, reinterpret_cast<unsigned long long>(s.list), src));
+    const int c = __shfl_sync(kFullMask, s.cnt, src);
+    float nt;
+    int nc;
+    warp_compact(l, c, kprime, lane, nt, nc);
+    if (lane == src) {
+      s.thr = fmaxf(s.thr, nt);
+      s.cnt = nc;
+    }
+  }
+}
+
+}  // namespace rbk

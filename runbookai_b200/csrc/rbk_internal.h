@@ -15,10 +15,16 @@ constexpr int kListCap = 256;     // entries per (CTA, query) candidate list
 constexpr int kMaxKPrime = 128;   // candidates kept per query (k_fetch + margin)
 constexpr int kScanThreads = 192; // warp0 TMA, warp1 MMA/TMEM, warps2-5 epilogue
 constexpr int kMaxSubBatch = 1024;  // queries per scan launch (8 query blocks)
+constexpr int kMaxLeadTiles = 8;    // lockstep: max tiles a CTA may lead the slowest peer of its range
+constexpr int kHistBins = 1024;     // per-query score histogram, cosine in [-1,1] -> bin width 1/512
 
 struct ScanParams {
   const float* inv_norm_c;  // [rows padded to kBlockN], NaN = dead / out of range
   const float* thr_init;    // [B] initial threshold, raw domain (acc * inv_norm_c); -inf = none
+  const float* inv_norm_q;  // [B] 1/||bf16(q)||
+  unsigned int* hist;       // [B][kHistBins] scores of all appended rows (zeroed per launch)
+  int* maxbin;              // [B] highest occupied histogram bin (zeroed per launch)
+  int* progress;            // [R][QB] tiles issued by each CTA's producer (zeroed per launch)
   unsigned long long* cand; // [QB][R][kBlockM][kListCap] packed keys
   int* cand_cnt;            // [QB][R][kBlockM]
   float* dbg_scores;        // nullable: [B][n_rows] raw-domain scores (validation aid)

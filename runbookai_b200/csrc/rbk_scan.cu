@@ -16,6 +16,7 @@
 //   (1 thread), warps 2..5 = epilogue (TMEM lane quadrant = warp % 4).
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM double buffer full/empty
 //   (MMA <-> epilogue): the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "rbk_epilogue.cuh"
 #include "rbk_internal.h"
 #include "rbk_ptx.cuh"
 
@@ -38,69 +39,6 @@ struct SmemTail {
   unsigned long long tmem_empty[2];
   uint32_t tmem_base;
 };
-
-__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) {
-  return a > b ? a : b;
-}
-__device__ __forceinline__ unsigned long long umin64(unsigned long long a, unsigned long long b) {
-  return a < b ? a : b;
-}
-
-// Warp-cooperative compaction of one query's candidate list: bitonic sort of up to 256
-// keys (8 per lane, element i = j*32 + lane), keep the best k', return the k'-th score.
-__device__ __noinline__ void warp_compact(unsigned long long* list, int cnt, int kprime, int lane, float& new_thr,
-                                          int& new_cnt) {
-  unsigned long long k[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int idx = j * 32 + lane;
-    k[j] = idx < cnt ? __ldcg(list + idx) : 0ull;
-  }
-#pragma unroll
-  for (int k2 = 2; k2 <= 256; k2 <<= 1) {
-#pragma unroll
-    for (int s = k2 >> 1; s > 0; s >>= 1) {
-      if (s >= 32) {
-        const int js = s >> 5;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if ((j & js) == 0) {
-            const int i = j * 32 + lane;
-            const bool desc = (i & k2) == 0;
-            const unsigned long long a = k[j], b = k[j | js];
-            const unsigned long long hi = umax64(a, b), lo = umin64(a, b);
-            k[j] = desc ? hi : lo;
-            k[j | js] = desc ? lo : hi;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int i = j * 32 + lane;
-          const unsigned long long other = __shfl_xor_sync(kFull, k[j], s);
-          const bool lower = (lane & s) == 0;
-          const bool desc = (i & k2) == 0;
-          k[j] = (lower == desc) ? umax64(k[j], other) : umin64(k[j], other);
-        }
-      }
-    }
-  }
-  const int keep = cnt < kprime ? cnt : kprime;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int idx = j * 32 + lane;
-    if (idx < keep) list[idx] = k[j];
-  }
-  const int e = kprime - 1;
-  unsigned long long sel = 0ull;
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    if (j == (e >> 5)) sel = k[j];
-  const unsigned long long kth = __shfl_sync(kFull, sel, e & 31);
-  new_thr = cnt >= kprime ? key_score(kth) : -INFINITY;
-  new_cnt = keep;
-  __syncwarp();
-}
 
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
@@ -145,7 +83,23 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
+      volatile int* prog = p.progress + r * p.QB;
       for (int tile = t0; tile < t1; ++tile) {
+        // Bounded-lag lockstep of the QB CTAs that stream the same corpus range: nobody runs
+        // more than kMaxLeadTiles ahead of the slowest, so a tile pulled from HBM by the
+        // first reader is still in L2 for the others (keeps DRAM traffic ~1x the corpus).
+        const int it = tile - t0;
+        if (p.QB > 1 && (it & 1) == 0) {
+          prog[qb] = it;
+          for (int o = 0; o < p.QB; ++o) {
+            if (o == qb) continue;
+            const long long w0 = clock64();
+            while (prog[o] < it - kMaxLeadTiles) {
+              __nanosleep(200);
+              if (clock64() - w0 > (1ll << 31)) __trap();
+            }
+          }
+        }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
           const uint32_t full = smem_u32(&tail->full[s]);
@@ -156,6 +110,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
           if (++s == kStages) { s = 0; ph ^= 1u; }
         }
       }
+      if (p.QB > 1) prog[qb] = 0x7FFFFFFF;  // done: never hold a peer back
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
@@ -192,10 +147,10 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
     const int q = qb * kBlockM + qrow;
     const bool q_valid = q < p.B;
     const int et = threadIdx.x - 64;      // 0..127
-    float thr = q_valid ? p.thr_init[q] : INFINITY;
-    int cnt = 0;
-    unsigned long long* list =
-        p.cand + (static_cast<size_t>(qb * p.R + r) * kBlockM + qrow) * static_cast<size_t>(kListCap);
+    FilterState fs;
+    filter_init(fs, q_valid, q_valid ? p.thr_init[q] : INFINITY, q_valid ? p.inv_norm_q[q] : 0.f,
+                p.cand + (static_cast<size_t>(qb * p.R + r) * kBlockM + qrow) * static_cast<size_t>(kListCap),
+                p.hist + static_cast<size_t>(q_valid ? q : 0) * kHistBins, p.maxbin + (q_valid ? q : 0));
     int as = 0;
     uint32_t aph = 0;
     for (int tile = t0; tile < t1; ++tile) {
@@ -205,6 +160,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
       tail->invc[as][et] = ic0;
       tail->invc[as][kEpiThreads + et] = ic1;
       named_bar_sync(1, kEpiThreads);
+      if (tile != t0) filter_refresh(fs, p.kprime);   // overlaps the MMAs of this tile
       mbar_wait(smem_u32(&tail->tmem_full[as]), aph);
       tc_fence_after();
       const float* invc = tail->invc[as];
@@ -215,27 +171,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                                static_cast<uint32_t>(as * kBlockN + chunk * 32),
                            v);
         tmem_wait_ld();
-        const float4* ic4 = reinterpret_cast<const float4*>(invc + chunk * 32);
-        float m = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 w = ic4[j];
-          const float a0 = __uint_as_float(v[4 * j + 0]) * w.x;
-          const float a1 = __uint_as_float(v[4 * j + 1]) * w.y;
-          const float a2 = __uint_as_float(v[4 * j + 2]) * w.z;
-          const float a3 = __uint_as_float(v[4 * j + 3]) * w.w;
-          m = fmaxf(m, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));  // fmaxf drops NaN (dead rows)
-        }
-        if (m > thr) {  // rare: at least one survivor in this chunk for this query
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float t = __uint_as_float(v[j]) * invc[chunk * 32 + j];
-            if (t > thr) {
-              list[cnt] = pack_key(t, static_cast<uint32_t>(row0 + chunk * 32 + j));
-              ++cnt;
-            }
-          }
-        }
+        filter_chunk(fs, v, invc + chunk * 32, static_cast<uint32_t>(row0 + chunk * 32));
         if (p.dbg_scores != nullptr && q_valid) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -244,22 +180,8 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
               p.dbg_scores[static_cast<size_t>(q) * p.n_rows + row] = __uint_as_float(v[j]) * invc[chunk * 32 + j];
           }
         }
-        __syncwarp();
-        unsigned need = __ballot_sync(kFull, cnt > kListCap - 32);
-        while (need) {
-          const int src = __ffs(need) - 1;
-          need &= need - 1;
-          unsigned long long* l =
-              reinterpret_cast<unsigned long long*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(list), src));
-          const int c = __shfl_sync(kFull, cnt, src);
-          float nt;
-          int nc;
-          warp_compact(l, c, p.kprime, lane, nt, nc);
-          if (lane == src) {
-            thr = fmaxf(thr, nt);
-            cnt = nc;
-          }
-        }
+        filter_compact_if_needed(fs, p.kprime, lane);
+        if (tile == t0) filter_refresh(fs, p.kprime);   // start-up: converge within the first tile
       }
       tc_fence_before();
       __syncwarp();
@@ -267,7 +189,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
       as ^= 1;
       if (as == 0) aph ^= 1u;
     }
-    p.cand_cnt[(qb * p.R + r) * kBlockM + qrow] = cnt;
+    p.cand_cnt[(qb * p.R + r) * kBlockM + qrow] = fs.cnt;
   }
 
   tc_fence_before();

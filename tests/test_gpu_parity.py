@@ -216,7 +216,7 @@ def test_degenerate_inputs_and_errors(rb, native):
 
 
 def test_threshold_inclusive_on_gpu(rb):
-    rows = np.array([[1.0, 1, 1, 1], [1.0, 1, 1, 2], [1.0, 0, 1, 0]])
+    rows = np.array([[1.0, 1, 1, 1], [1.0, 1, 1, 2], [0.0, 1, 1, 0]])
     with rb.Index(4) as ix:
         ix.append_f64(rows)
         s, v, c, _ = ix.search(np.array([[1.0, 0, 0, 0]]), 8, 0.5)
