@@ -144,7 +144,8 @@ struct rbk_index {
   PinBuf<long long> h_slots;
   PinBuf<double> h_scores;
   PinBuf<float> h_f32;
-  CUtensorMap tmap_c;
+  CUtensorMap tmap_c, tmap_c_half;
+  bool force_1cta = false;
   const void* tmap_c_base = nullptr;
   int64_t tmap_c_rows = -1;
   std::vector<cudaEvent_t> ev;
@@ -269,6 +270,8 @@ rbk_status refresh_corpus_tmap(rbk_index* ix) {
   if (ix->tmap_c_base == ix->rows && ix->tmap_c_rows == ix->n_rows) return RBK_OK;
   rbk_status st = encode_rows_tmap(&ix->tmap_c, ix->rows, ix->n_rows, ix->dpad, kBlockN);
   if (st != RBK_OK) return st;
+  st = encode_rows_tmap(&ix->tmap_c_half, ix->rows, ix->n_rows, ix->dpad, kBlockN / 2);
+  if (st != RBK_OK) return st;
   ix->tmap_c_base = ix->rows;
   ix->tmap_c_rows = ix->n_rows;
   return RBK_OK;
@@ -324,8 +327,12 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
   const int n_tiles = static_cast<int>((ix->n_rows + kBlockN - 1) / kBlockN);
   for (int q0 = 0; q0 < B; q0 += kMaxSubBatch) {
     const int Bs = std::min(kMaxSubBatch, B - q0);
-    const int QB = (Bs + kBlockM - 1) / kBlockM;
-    int R = std::max(1, std::min(ix->sm_count / QB, n_tiles));
+    // more than one 128-query block: CTA pairs (256 queries per pair) halve the corpus bytes per query
+    const bool pairs = Bs > kBlockM && !ix->force_1cta;
+    const int block_m = pairs ? 2 * kBlockM : kBlockM;
+    const int QB = (Bs + block_m - 1) / block_m;
+    const int units = pairs ? ix->sm_count / 2 : ix->sm_count;
+    int R = std::max(1, std::min(units / QB, n_tiles));
     CUtensorMap tmap_q;
     st = encode_rows_tmap(&tmap_q, ix->q_bf16.p + static_cast<size_t>(q0) * ix->dpad, Bs, ix->dpad, kBlockM);
     if (st != RBK_OK) return st;
@@ -350,7 +357,8 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
     sp.R = R;
     sp.n_tiles = n_tiles;
     CK(cudaEventRecord(get_event(ix, (*ev_cursor)++), ix->stream));
-    CK(launch_scan(tmap_q, ix->tmap_c, sp, ix->stream));
+    if (pairs) CK(launch_scan2(tmap_q, ix->tmap_c_half, sp, ix->stream));
+    else CK(launch_scan(tmap_q, ix->tmap_c, sp, ix->stream));
     CK(cudaEventRecord(get_event(ix, (*ev_cursor)++), ix->stream));
     ix->stats.scan_launches++;
     ix->stats.kernel_launches++;
@@ -366,6 +374,7 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
       fp.d = ix->dim;
       fp.dpad = ix->dpad;
       fp.q0 = q0;
+      fp.block_m = block_m;
       fp.min_score = min_score;
       fp.rows = ix->rows;
       fp.row_norm2 = ix->norm2;
@@ -535,6 +544,7 @@ rbk_status rbk_index_create(int32_t dim, int32_t device, int64_t capacity_hint, 
   memset(&ix->stats, 0, sizeof ix->stats);
   ix->stats.sm_count = ix->sm_count;
   if (const char* m = getenv("RBK_KNN_MARGIN")) ix->margin = std::max(0, std::min(96, atoi(m)));
+  if (const char* m = getenv("RBK_KNN_FORCE_1CTA")) ix->force_1cta = atoi(m) != 0;   // A/B measurements only
   e = cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     delete ix;

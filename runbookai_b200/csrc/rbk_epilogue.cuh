@@ -55,7 +55,7 @@ __device__ __forceinline__ void filter_init(FilterState& s, bool valid, float th
 }
 
 // Raise thr from the global histogram (source 3).  Per-thread, no warp collectives.
-__device__ __noinline__ void filter_refresh(FilterState& s, int kprime) {
+static __device__ __noinline__ void filter_refresh(FilterState& s, int kprime) {
   if (!s.valid) return;
   const int mb = __ldcg(s.maxbin_q);
   if (mb <= s.tb) return;
@@ -129,7 +129,7 @@ __device__ __forceinline__ unsigned long long umin64(unsigned long long a, unsig
 
 // Warp-cooperative compaction of one list: bitonic sort of up to 256 keys (8 per lane,
 // element i = j*32 + lane), keep the best k', return the k'-th score (source 2).
-__device__ __noinline__ void warp_compact(unsigned long long* list, int cnt, int kprime, int lane, float& new_thr,
+static __device__ __noinline__ void warp_compact(unsigned long long* list, int cnt, int kprime, int lane, float& new_thr,
                                           int& new_cnt) {
   constexpr uint32_t kFullMask = 0xFFFFFFFFu;
   unsigned long long k[8];

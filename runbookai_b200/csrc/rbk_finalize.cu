@@ -127,11 +127,11 @@ constexpr int kFinThreads = 256;
 // Visit every candidate key of one query: lists (qb, r, qrow) for r in [0, R).
 template <typename F>
 __device__ __forceinline__ void for_each_key(const unsigned long long* __restrict__ cand, const int* s_cnt, int QB, int R,
-                                             int qb, int qrow, F&& f) {
+                                             int qb, int qrow, int block_m, F&& f) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int r = warp; r < R; r += kFinThreads / 32) {
     const unsigned long long* l =
-        cand + (static_cast<size_t>(qb * R + r) * kBlockM + qrow) * static_cast<size_t>(kListCap);
+        cand + (static_cast<size_t>(qb * R + r) * block_m + qrow) * static_cast<size_t>(kListCap);
     const int c = s_cnt[r];
     for (int i = lane; i < c; i += 32) f(__ldcg(l + i));
   }
@@ -141,7 +141,7 @@ __device__ __forceinline__ void for_each_key(const unsigned long long* __restric
 __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p) {
   const int ql = blockIdx.x;  // query index inside this launch
   const int tid = threadIdx.x;
-  const int qb = ql / kBlockM, qrow = ql % kBlockM;
+  const int qb = ql / p.block_m, qrow = ql % p.block_m;
 
   __shared__ int s_cnt[160];
   __shared__ unsigned int s_hist[256];
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p)
   __syncthreads();
   int local = 0;
   for (int r = tid; r < p.R; r += kFinThreads) {
-    const int c = p.cand_cnt[(qb * p.R + r) * kBlockM + qrow];
+    const int c = p.cand_cnt[(qb * p.R + r) * p.block_m + qrow];
     s_cnt[r] = c;
     local += c;
   }
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p)
       s_hist[tid] = 0u;
       __syncthreads();
       const unsigned long long prefix = s_prefix;
-      for_each_key(p.cand, s_cnt, p.QB, p.R, qb, qrow, [&](unsigned long long k) {
+      for_each_key(p.cand, s_cnt, p.QB, p.R, qb, qrow, p.block_m, [&](unsigned long long k) {
         if ((k & mask) == prefix) atomicAdd(&s_hist[static_cast<unsigned>(k >> shift) & 255u], 1u);
       });
       __syncthreads();
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p)
     }
     pivot = s_prefix;
   }
-  for_each_key(p.cand, s_cnt, p.QB, p.R, qb, qrow, [&](unsigned long long k) {
+  for_each_key(p.cand, s_cnt, p.QB, p.R, qb, qrow, p.block_m, [&](unsigned long long k) {
     if (k >= pivot) {
       const int pos = atomicAdd(&s_nsel, 1);
       if (pos < kMaxKPrime) s_sel[pos] = k;

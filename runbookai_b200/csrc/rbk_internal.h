@@ -40,6 +40,10 @@ struct ScanParams {
 cudaError_t launch_scan(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const ScanParams& p,
                         cudaStream_t stream);
 size_t scan_smem_bytes();
+// CTA-pair variant (B > 128): QB counts 256-query blocks, R pairs per block; tmap_c_half has 128-row boxes.
+cudaError_t launch_scan2(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c_half, const ScanParams& p,
+                         cudaStream_t stream);
+size_t scan2_smem_bytes();
 
 // ---- ingest (rbk_ingest.cu) ----
 // src element type: 0 = f64, 1 = f32, 2 = bf16 bits.  src is device memory, row pitch = d.
@@ -67,6 +71,7 @@ struct FinalizeParams {
   const unsigned long long* cand;
   const int* cand_cnt;
   int QB, R, kprime, k_fetch, B, d, dpad;
+  int block_m;  // queries per list block: 128 (1-CTA scan) or 256 (CTA-pair scan)
   int q0;  // global index of the first query of this launch (sub-batch offset)
   double min_score;
   const uint16_t* rows;

@@ -150,8 +150,9 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 // Arrive on the barrier at the same offset in the leader CTA (works from either CTA).
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t local_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(local_bar & kPeerBitMask)
-               : "memory");
+  // default semantics (release at CTA scope): a cluster-scope release would drag in a
+  // MEMBAR.GPU + ERRBAR per arrive (seen in the ncu source view) for no benefit here
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(local_bar & kPeerBitMask) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t smem_result_addr, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result_addr),
