@@ -53,16 +53,21 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2D bf16 row-major [rows][dpad] tensor, box = 64 columns (128 B, one swizzle row) x box_rows.
-rbk_status encode_rows_tmap(CUtensorMap* out, const void* base, int64_t rows, int dpad, int box_rows) {
+// 2D bf16 row-major [rows][dpad] tensor, box = box_cols columns (one swizzle row: 64 -> 128 B, 32 -> 64 B)
+// x box_rows.
+rbk_status encode_rows_tmap(CUtensorMap* out, const void* base, int64_t rows, int dpad, int box_rows,
+                            int box_cols = kBlockK) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(RBK_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(dpad), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(dpad) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                 : (box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE),
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[160];
@@ -144,8 +149,9 @@ struct rbk_index {
   PinBuf<long long> h_slots;
   PinBuf<double> h_scores;
   PinBuf<float> h_f32;
-  CUtensorMap tmap_c, tmap_c_half;
-  bool force_1cta = false;
+  CUtensorMap tmap_c, tmap_c_half, tmap_c_half32, tmap_c_pf;
+  bool force_1cta = false, force_streamed = true;   // query-resident pair kernel: measured slower
+  int prefetch_tiles = 0;
   const void* tmap_c_base = nullptr;
   int64_t tmap_c_rows = -1;
   std::vector<cudaEvent_t> ev;
@@ -272,6 +278,10 @@ rbk_status refresh_corpus_tmap(rbk_index* ix) {
   if (st != RBK_OK) return st;
   st = encode_rows_tmap(&ix->tmap_c_half, ix->rows, ix->n_rows, ix->dpad, kBlockN / 2);
   if (st != RBK_OK) return st;
+  st = encode_rows_tmap(&ix->tmap_c_half32, ix->rows, ix->n_rows, ix->dpad, kBlockN / 2, 32);
+  if (st != RBK_OK) return st;
+  st = encode_rows_tmap(&ix->tmap_c_pf, ix->rows, ix->n_rows, ix->dpad, kBlockN / 2, 256);
+  if (st != RBK_OK) return st;
   ix->tmap_c_base = ix->rows;
   ix->tmap_c_rows = ix->n_rows;
   return RBK_OK;
@@ -353,11 +363,16 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
     sp.B = Bs;
     sp.kprime = kprime;
     sp.num_kb = (ix->dpad + kBlockK - 1) / kBlockK;
+    sp.dpad = ix->dpad;
     sp.QB = QB;
     sp.R = R;
     sp.n_tiles = n_tiles;
     CK(cudaEventRecord(get_event(ix, (*ev_cursor)++), ix->stream));
-    if (pairs) CK(launch_scan2(tmap_q, ix->tmap_c_half, sp, ix->stream));
+    const bool resident = pairs && !ix->force_streamed && scan2_resident_fits(ix->dpad);
+    sp.prefetch_tiles = ix->prefetch_tiles;
+    if (pairs)
+      CK(launch_scan2(tmap_q, (resident && scan2_resident_k() == 32) ? ix->tmap_c_half32 : ix->tmap_c_half,
+                      ix->tmap_c_pf, sp, resident, ix->stream));
     else CK(launch_scan(tmap_q, ix->tmap_c, sp, ix->stream));
     CK(cudaEventRecord(get_event(ix, (*ev_cursor)++), ix->stream));
     ix->stats.scan_launches++;
@@ -545,6 +560,8 @@ rbk_status rbk_index_create(int32_t dim, int32_t device, int64_t capacity_hint, 
   ix->stats.sm_count = ix->sm_count;
   if (const char* m = getenv("RBK_KNN_MARGIN")) ix->margin = std::max(0, std::min(96, atoi(m)));
   if (const char* m = getenv("RBK_KNN_FORCE_1CTA")) ix->force_1cta = atoi(m) != 0;   // A/B measurements only
+  if (const char* m = getenv("RBK_KNN_RESIDENT")) ix->force_streamed = atoi(m) == 0;   // experiments only
+  if (const char* m = getenv("RBK_KNN_PREFETCH_TILES")) ix->prefetch_tiles = std::max(0, std::min(64, atoi(m)));
   e = cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     delete ix;

@@ -205,4 +205,84 @@ __device__ __forceinline__ void filter_compact_if_needed(FilterState& s, int kpr
   }
 }
 
+
+// The whole epilogue role (4 warps, 128 threads, thread <-> query) shared by the scan
+// kernels.  kPair: CTA-pair kernels (256-query blocks, remote arrive on the leader's
+// tmem_empty barrier).  invc: per-accumulator-stage staging of the tile's 1/||c||.
+template <bool kPair>
+__device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_stage)[kBlockN],
+                                             unsigned long long* tmem_full, unsigned long long* tmem_empty,
+                                             uint32_t tmem_base, int qb, int r, uint32_t rank, int t0, int t1,
+                                             int warp, int lane) {
+  constexpr int kEpi = 128;
+  constexpr int kBlockQ = kPair ? 2 * kBlockM : kBlockM;
+  const int quad = warp & 3;            // TMEM lane quadrant this warp may read
+  const int qrow = quad * 32 + lane;    // TMEM lane
+  const int qin = (kPair ? static_cast<int>(rank) * kBlockM : 0) + qrow;   // row inside the query block
+  const int q = qb * kBlockQ + qin;
+  const bool q_valid = q < p.B;
+  const int et = threadIdx.x - 64;      // 0..127
+  FilterState fs;
+  filter_init(fs, q_valid, q_valid ? p.thr_init[q] : INFINITY, q_valid ? p.inv_norm_q[q] : 0.f,
+              p.cand + (static_cast<size_t>(qb * p.R + r) * kBlockQ + qin) * static_cast<size_t>(kListCap),
+              p.hist + static_cast<size_t>(q_valid ? q : 0) * kHistBins, p.maxbin + (q_valid ? q : 0));
+  int as = 0;
+  uint32_t aph = 0;
+  for (int tile = t0; tile < t1; ++tile) {
+    const int row0 = tile * kBlockN;
+    const int it = tile - t0;
+    float* invc = invc_stage[as];
+    invc[et] = __ldg(p.inv_norm_c + row0 + et);
+    invc[kEpi + et] = __ldg(p.inv_norm_c + row0 + kEpi + et);
+    named_bar_sync(1, kEpi);
+    if (it != 0 && (it < 8 || (it & 3) == 0)) filter_refresh(fs, p.kprime);   // overlaps this tile's MMAs
+    mbar_wait(smem_u32(&tmem_full[as]), aph);
+    tc_fence_after();
+#pragma unroll 1
+    for (int chunk = 0; chunk < kBlockN / 32; ++chunk) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                             static_cast<uint32_t>(as * kBlockN + chunk * 32),
+                         v);
+      tmem_wait_ld();
+      filter_chunk(fs, v, invc + chunk * 32, static_cast<uint32_t>(row0 + chunk * 32));
+      if (p.dbg_scores != nullptr && q_valid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int row = row0 + chunk * 32 + j;
+          if (row < p.n_rows)
+            p.dbg_scores[static_cast<size_t>(q) * p.n_rows + row] = __uint_as_float(v[j]) * invc[chunk * 32 + j];
+        }
+      }
+      filter_compact_if_needed(fs, p.kprime, lane);
+      if (it == 0) filter_refresh(fs, p.kprime);   // start-up: converge within the first tile
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if (kPair) mbar_arrive_leader(smem_u32(&tmem_empty[as]));
+      else mbar_arrive(smem_u32(&tmem_empty[as]));
+    }
+    as ^= 1;
+    if (as == 0) aph ^= 1u;
+  }
+  p.cand_cnt[(qb * p.R + r) * kBlockQ + qin] = fs.cnt;
+}
+
+// Bounded-lag lockstep of the QB producers that stream the same corpus range: nobody runs
+// more than kMaxLeadTiles ahead of the slowest, so a tile pulled from HBM by the first
+// reader is still in L2 for the others (keeps DRAM traffic close to 1x the corpus).
+__device__ __forceinline__ void lockstep_pace(volatile int* prog, int QB, int qb, int it) {
+  if (QB <= 1 || (it & 1) != 0) return;
+  prog[qb] = it;
+  for (int o = 0; o < QB; ++o) {
+    if (o == qb) continue;
+    const long long w0 = clock64();
+    while (prog[o] < it - kMaxLeadTiles) {
+      __nanosleep(200);
+      if (clock64() - w0 > (1ll << 24)) break;   // a pacing hint, never a correctness wait
+    }
+  }
+}
+
 }  // namespace rbk

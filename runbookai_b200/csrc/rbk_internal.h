@@ -32,6 +32,8 @@ struct ScanParams {
   int B;        // queries in this launch
   int kprime;
   int num_kb;   // k-blocks per tile = ceil(dpad / kBlockK)
+  int dpad;     // padded row length (elements)
+  int prefetch_tiles;  // query-resident pair kernel: L2 prefetch distance in tiles (0 = off)
   int QB;       // query blocks
   int R;        // corpus ranges (CTAs per query block)
   int n_tiles;  // ceil(n_rows / kBlockN)
@@ -40,10 +42,13 @@ struct ScanParams {
 cudaError_t launch_scan(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const ScanParams& p,
                         cudaStream_t stream);
 size_t scan_smem_bytes();
-// CTA-pair variant (B > 128): QB counts 256-query blocks, R pairs per block; tmap_c_half has 128-row boxes.
-cudaError_t launch_scan2(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c_half, const ScanParams& p,
-                         cudaStream_t stream);
-size_t scan2_smem_bytes();
+// CTA-pair variants (B > 128): QB counts 256-query blocks, R pairs per block.  tmap_c has 128-row boxes:
+// 64 columns / SWIZZLE_128B for the streamed kernel, 32 columns / SWIZZLE_64B for the query-resident one.
+// tmap_pf: un-swizzled 128-row x 256-col boxes, used only for L2 prefetch.
+cudaError_t launch_scan2(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const CUtensorMap& tmap_pf,
+                         const ScanParams& p, bool resident, cudaStream_t stream);
+bool scan2_resident_fits(int dpad);
+int scan2_resident_k();   // corpus columns per stage of the resident kernel (64 or 32)
 
 // ---- ingest (rbk_ingest.cu) ----
 // src element type: 0 = f64, 1 = f32, 2 = bf16 bits.  src is device memory, row pitch = d.

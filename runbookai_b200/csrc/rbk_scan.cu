@@ -28,7 +28,6 @@ constexpr int kABytes = kBlockM * kBlockK * 2;      // 16 KiB  query k-slab
 constexpr int kBBytes = kBlockN * kBlockK * 2;      // 32 KiB  corpus k-slab
 constexpr int kStageBytes = kABytes + kBBytes;      // 48 KiB
 constexpr int kTmemCols = 512;                      // 2 accumulator stages x 256 fp32 columns
-constexpr int kEpiThreads = 128;
 
 struct SmemTail {
   float invc[2][kBlockN];  // 1/||c|| of the tile's rows, per accumulator stage
@@ -84,21 +83,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
       uint32_t ph = 0;
       volatile int* prog = p.progress + r * p.QB;
       for (int tile = t0; tile < t1; ++tile) {
-        // Bounded-lag lockstep of the QB CTAs that stream the same corpus range: nobody runs
-        // more than kMaxLeadTiles ahead of the slowest, so a tile pulled from HBM by the
-        // first reader is still in L2 for the others (keeps DRAM traffic ~1x the corpus).
-        const int it = tile - t0;
-        if (p.QB > 1 && (it & 1) == 0) {
-          prog[qb] = it;
-          for (int o = 0; o < p.QB; ++o) {
-            if (o == qb) continue;
-            const long long w0 = clock64();
-            while (prog[o] < it - kMaxLeadTiles) {
-              __nanosleep(200);
-              if (clock64() - w0 > (1ll << 24)) break;   // a pacing hint, never a correctness wait
-            }
-          }
-        }
+        lockstep_pace(prog, p.QB, qb, tile - t0);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
           const uint32_t full = smem_u32(&tail->full[s]);
@@ -141,57 +126,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue: thread <-> query =====================
-    const int quad = warp & 3;            // TMEM lane quadrant this warp may read
-    const int qrow = quad * 32 + lane;    // row of the 128-query block == TMEM lane
-    const int q = qb * kBlockM + qrow;
-    const bool q_valid = q < p.B;
-    const int et = threadIdx.x - 64;      // 0..127
-    FilterState fs;
-    filter_init(fs, q_valid, q_valid ? p.thr_init[q] : INFINITY, q_valid ? p.inv_norm_q[q] : 0.f,
-                p.cand + (static_cast<size_t>(qb * p.R + r) * kBlockM + qrow) * static_cast<size_t>(kListCap),
-                p.hist + static_cast<size_t>(q_valid ? q : 0) * kHistBins, p.maxbin + (q_valid ? q : 0));
-    int as = 0;
-    uint32_t aph = 0;
-    for (int tile = t0; tile < t1; ++tile) {
-      const int row0 = tile * kBlockN;
-      const float ic0 = __ldg(p.inv_norm_c + row0 + et);
-      const float ic1 = __ldg(p.inv_norm_c + row0 + kEpiThreads + et);
-      tail->invc[as][et] = ic0;
-      tail->invc[as][kEpiThreads + et] = ic1;
-      named_bar_sync(1, kEpiThreads);
-      {
-        const int it = tile - t0;
-        if (it != 0 && (it < 8 || (it & 3) == 0)) filter_refresh(fs, p.kprime);   // overlaps this tile's MMAs
-      }
-      mbar_wait(smem_u32(&tail->tmem_full[as]), aph);
-      tc_fence_after();
-      const float* invc = tail->invc[as];
-#pragma unroll 1
-      for (int chunk = 0; chunk < kBlockN / 32; ++chunk) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                               static_cast<uint32_t>(as * kBlockN + chunk * 32),
-                           v);
-        tmem_wait_ld();
-        filter_chunk(fs, v, invc + chunk * 32, static_cast<uint32_t>(row0 + chunk * 32));
-        if (p.dbg_scores != nullptr && q_valid) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int row = row0 + chunk * 32 + j;
-            if (row < p.n_rows)
-              p.dbg_scores[static_cast<size_t>(q) * p.n_rows + row] = __uint_as_float(v[j]) * invc[chunk * 32 + j];
-          }
-        }
-        filter_compact_if_needed(fs, p.kprime, lane);
-        if (tile == t0) filter_refresh(fs, p.kprime);   // start-up: converge within the first tile
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tail->tmem_empty[as]));
-      as ^= 1;
-      if (as == 0) aph ^= 1u;
-    }
-    p.cand_cnt[(qb * p.R + r) * kBlockM + qrow] = fs.cnt;
+    run_epilogue<false>(p, tail->invc, tail->tmem_full, tail->tmem_empty, tmem_base, qb, r, 0u, t0, t1, warp, lane);
   }
 
   tc_fence_before();
