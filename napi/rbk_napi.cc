@@ -1,0 +1,227 @@
+// rbk_napi.cc — thin Node N-API addon over include/rbk_knn.h (librbk_knn.so).
+//
+// NOT COMPILED in the build image (no node, no node_api.h): committed as the binding a
+// RunbookAI maintainer adds next to better-sqlite3.  Logic-free by design: every method
+// maps 1:1 onto a C-ABI call; errors become `new Error(rbk_last_error())` (sync methods
+// throw, `search` rejects its Promise), the convention the reference already follows
+// (vector-store.ts:197-199, embedder.ts:169-171).
+//
+//   const { RbkIndex } = require('./build/Release/rbk_knn.node')
+//   const ix = new RbkIndex(dim, device)
+//   ix.appendF64(Float64Array rows)            -> firstSlot
+//   ix.overwriteF64(slot, Float64Array row); ix.tombstone(BigInt64Array slots); ix.clear()
+//   await ix.search(Float64Array queries, B, kFetch, minScore)
+//        -> { slots: BigInt64Array, scores: Float64Array, counts: Int32Array }
+//
+// Build (where Node headers exist):  node-gyp with  libraries: ["-lrbk_knn"], include_dirs: ["../include"].
+#include <node_api.h>
+
+#include <cmath>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../include/rbk_knn.h"
+
+namespace {
+
+#define NAPI_OK(call)                                        \
+  if ((call) != napi_ok) {                                   \
+    napi_throw_error(env, nullptr, "N-API call failed: " #call); \
+    return nullptr;                                          \
+  }
+
+napi_value throw_rbk(napi_env env) {
+  napi_throw_error(env, nullptr, rbk_last_error());
+  return nullptr;
+}
+
+rbk_index* unwrap(napi_env env, napi_callback_info info, size_t* argc, napi_value* argv) {
+  napi_value self;
+  void* p = nullptr;
+  if (napi_get_cb_info(env, info, argc, argv, &self, nullptr) != napi_ok) return nullptr;
+  if (napi_unwrap(env, self, &p) != napi_ok) return nullptr;
+  return static_cast<rbk_index*>(p);
+}
+
+void finalize_index(napi_env, void* data, void*) { rbk_index_destroy(static_cast<rbk_index*>(data)); }
+
+napi_value New(napi_env env, napi_callback_info info) {
+  size_t argc = 3;
+  napi_value argv[3], self;
+  NAPI_OK(napi_get_cb_info(env, info, &argc, argv, &self, nullptr));
+  int32_t dim = 0, device = 0;
+  int64_t hint = 0;
+  NAPI_OK(napi_get_value_int32(env, argv[0], &dim));
+  if (argc > 1) napi_get_value_int32(env, argv[1], &device);
+  if (argc > 2) napi_get_value_int64(env, argv[2], &hint);
+  rbk_index* ix = nullptr;
+  if (rbk_index_create(dim, device, hint, &ix) != RBK_OK) return throw_rbk(env);   // no GPU -> throws, no fallback
+  NAPI_OK(napi_wrap(env, self, ix, finalize_index, nullptr, nullptr));
+  return self;
+}
+
+napi_value AppendF64(napi_env env, napi_callback_info info) {
+  size_t argc = 1;
+  napi_value argv[1];
+  rbk_index* ix = unwrap(env, info, &argc, argv);
+  napi_typedarray_type t;
+  size_t len;
+  void* data;
+  NAPI_OK(napi_get_typedarray_info(env, argv[0], &t, &len, &data, nullptr, nullptr));
+  if (t != napi_float64_array || len % rbk_index_dim(ix) != 0) {
+    napi_throw_error(env, nullptr, "Vectors must have the same length");
+    return nullptr;
+  }
+  int64_t first = -1;
+  if (rbk_index_append_f64(ix, static_cast<const double*>(data), (int64_t)(len / rbk_index_dim(ix)), &first) != RBK_OK)
+    return throw_rbk(env);
+  napi_value out;
+  NAPI_OK(napi_create_int64(env, first, &out));
+  return out;
+}
+
+napi_value OverwriteF64(napi_env env, napi_callback_info info) {
+  size_t argc = 2;
+  napi_value argv[2];
+  rbk_index* ix = unwrap(env, info, &argc, argv);
+  int64_t slot;
+  NAPI_OK(napi_get_value_int64(env, argv[0], &slot));
+  napi_typedarray_type t;
+  size_t len;
+  void* data;
+  NAPI_OK(napi_get_typedarray_info(env, argv[1], &t, &len, &data, nullptr, nullptr));
+  if (t != napi_float64_array || (int32_t)len != rbk_index_dim(ix)) {
+    napi_throw_error(env, nullptr, "Vectors must have the same length");
+    return nullptr;
+  }
+  if (rbk_index_overwrite_f64(ix, slot, static_cast<const double*>(data)) != RBK_OK) return throw_rbk(env);
+  return nullptr;
+}
+
+napi_value Tombstone(napi_env env, napi_callback_info info) {
+  size_t argc = 1;
+  napi_value argv[1];
+  rbk_index* ix = unwrap(env, info, &argc, argv);
+  napi_typedarray_type t;
+  size_t len;
+  void* data;
+  NAPI_OK(napi_get_typedarray_info(env, argv[0], &t, &len, &data, nullptr, nullptr));
+  if (t != napi_bigint64_array) {
+    napi_throw_type_error(env, nullptr, "slots must be a BigInt64Array");
+    return nullptr;
+  }
+  if (rbk_index_tombstone(ix, static_cast<const int64_t*>(data), (int64_t)len) != RBK_OK) return throw_rbk(env);
+  return nullptr;
+}
+
+napi_value Clear(napi_env env, napi_callback_info info) {
+  size_t argc = 0;
+  rbk_index* ix = unwrap(env, info, &argc, nullptr);
+  if (rbk_index_clear(ix) != RBK_OK) return throw_rbk(env);
+  return nullptr;
+}
+
+napi_value Count(napi_env env, napi_callback_info info) {
+  size_t argc = 0;
+  rbk_index* ix = unwrap(env, info, &argc, nullptr);
+  napi_value out;
+  NAPI_OK(napi_create_int64(env, rbk_index_count(ix), &out));
+  return out;
+}
+
+// ---- search: runs on a libuv worker so the JS thread never blocks on the GPU ----
+struct SearchJob {
+  rbk_index* ix;
+  std::vector<double> queries;
+  int32_t B, dim, k;
+  double min_score;
+  std::vector<int64_t> slots;
+  std::vector<double> scores;
+  std::vector<int32_t> counts;
+  rbk_status st = RBK_OK;
+  std::string err;
+  napi_deferred deferred;
+  napi_async_work work;
+};
+
+void search_execute(napi_env, void* data) {
+  SearchJob* j = static_cast<SearchJob*>(data);
+  j->st = rbk_index_search_f64(j->ix, j->queries.data(), j->B, j->dim, j->k, j->min_score, j->slots.data(),
+                               j->scores.data(), j->counts.data(), nullptr);
+  if (j->st != RBK_OK) j->err = rbk_last_error();   // thread-local: read it on the worker thread
+}
+
+void search_complete(napi_env env, napi_status, void* data) {
+  SearchJob* j = static_cast<SearchJob*>(data);
+  if (j->st != RBK_OK) {
+    napi_value msg, error;
+    napi_create_string_utf8(env, j->err.c_str(), NAPI_AUTO_LENGTH, &msg);
+    napi_create_error(env, nullptr, msg, &error);
+    napi_reject_deferred(env, j->deferred, error);
+  } else {
+    napi_value out, ab, ta;
+    void* p;
+    napi_create_object(env, &out);
+    napi_create_arraybuffer(env, j->slots.size() * 8, &p, &ab);
+    memcpy(p, j->slots.data(), j->slots.size() * 8);
+    napi_create_typedarray(env, napi_bigint64_array, j->slots.size(), ab, 0, &ta);
+    napi_set_named_property(env, out, "slots", ta);
+    napi_create_arraybuffer(env, j->scores.size() * 8, &p, &ab);
+    memcpy(p, j->scores.data(), j->scores.size() * 8);
+    napi_create_typedarray(env, napi_float64_array, j->scores.size(), ab, 0, &ta);
+    napi_set_named_property(env, out, "scores", ta);
+    napi_create_arraybuffer(env, j->counts.size() * 4, &p, &ab);
+    memcpy(p, j->counts.data(), j->counts.size() * 4);
+    napi_create_typedarray(env, napi_int32_array, j->counts.size(), ab, 0, &ta);
+    napi_set_named_property(env, out, "counts", ta);
+    napi_resolve_deferred(env, j->deferred, out);
+  }
+  napi_delete_async_work(env, j->work);
+  delete j;
+}
+
+napi_value Search(napi_env env, napi_callback_info info) {
+  size_t argc = 4;
+  napi_value argv[4];
+  rbk_index* ix = unwrap(env, info, &argc, argv);
+  napi_typedarray_type t;
+  size_t len;
+  void* data;
+  NAPI_OK(napi_get_typedarray_info(env, argv[0], &t, &len, &data, nullptr, nullptr));
+  auto* j = new SearchJob();
+  j->ix = ix;
+  napi_get_value_int32(env, argv[1], &j->B);
+  napi_get_value_int32(env, argv[2], &j->k);
+  napi_get_value_double(env, argv[3], &j->min_score);   // pass -Infinity for "no threshold"
+  j->dim = j->B > 0 ? (int32_t)(len / (size_t)j->B) : 0;   // a wrong length surfaces as RBK_EDIM
+  j->queries.assign(static_cast<double*>(data), static_cast<double*>(data) + len);
+  j->slots.resize((size_t)j->B * j->k);
+  j->scores.resize((size_t)j->B * j->k);
+  j->counts.resize((size_t)j->B);
+  napi_value promise, name;
+  NAPI_OK(napi_create_promise(env, &j->deferred, &promise));
+  napi_create_string_utf8(env, "rbk_search", NAPI_AUTO_LENGTH, &name);
+  NAPI_OK(napi_create_async_work(env, nullptr, name, search_execute, search_complete, j, &j->work));
+  NAPI_OK(napi_queue_async_work(env, j->work));
+  return promise;
+}
+
+napi_value Init(napi_env env, napi_value exports) {
+  napi_property_descriptor props[] = {
+      {"appendF64", nullptr, AppendF64, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"overwriteF64", nullptr, OverwriteF64, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"tombstone", nullptr, Tombstone, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"clear", nullptr, Clear, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"count", nullptr, Count, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"search", nullptr, Search, nullptr, nullptr, nullptr, napi_default, nullptr},
+  };
+  napi_value cls;
+  NAPI_OK(napi_define_class(env, "RbkIndex", NAPI_AUTO_LENGTH, New, nullptr, sizeof props / sizeof props[0], props, &cls));
+  NAPI_OK(napi_set_named_property(env, exports, "RbkIndex", cls));
+  return exports;
+}
+
+}  // namespace
+
+NAPI_MODULE(NODE_GYP_MODULE_NAME, Init)
