@@ -144,3 +144,41 @@ def test_vector_store_reload_is_rowid_order_and_errors(tmp_path):
     with pytest.raises(RuntimeError, match="Embedder not configured"):
         s2.search("redis")
     s2.close()
+
+
+def test_hybrid_retriever_modes_with_cpu_standin(tmp_path, oracle_mod):
+    """hybrid-search.ts:54-151 end to end on the host: FTS5 leg (SQLite) + vector leg (stand-in index) + RRF."""
+    from runbookai_b200 import embedder
+    from runbookai_b200.fts_store import KnowledgeStore
+    from runbookai_b200.hybrid_search import HybridRetriever, reciprocal_rank_fusion
+    from runbookai_b200.vector_store import VectorStore
+    embedder.configure(HashEmbedder(64))
+    fts = KnowledgeStore(str(tmp_path / "knowledge.db"))
+    docs = {"d1": ("runbook", "redis connection pool exhausted restart the pool"),
+            "d2": ("postmortem", "postgres replication lag after failover"),
+            "d3": ("runbook", "kubernetes pod crashloop out of memory")}
+    for did, (typ, text) in docs.items():
+        fts.upsert_document({"id": did, "type": typ, "title": did.upper(), "services": ["api"],
+                             "chunks": [{"id": f"{did}_{i}", "content": f"{text} step {i}", "sectionTitle": f"S{i}"}
+                                        for i in range(3)]})
+    h = HybridRetriever({"storePath": str(tmp_path / "knowledge.db"), "vectorStorePath": str(tmp_path / "vectors.db")},
+                        fts_store=fts)
+    h.vector_store.close()
+    h.vector_store = VectorStore(str(tmp_path / "vectors.db"), index_factory=lambda d, dev: OracleIndex(d))
+    for did, (typ, text) in docs.items():
+        h.vector_store.add_chunks([{"chunk": {"id": f"{did}_{i}", "documentId": did, "content": f"{text} step {i}",
+                                              "sectionTitle": f"S{i}"}, "documentTitle": did.upper(), "type": typ,
+                                    "services": ["api"]} for i in range(3)])
+    q = "redis connection pool"
+    f = h.search(q, {"mode": "fts", "topK": 4})
+    assert f and all(r.documentId == "d1" for r in f) and f[0].sourceUrl is None
+    v = h.search(q, {"mode": "vector", "topK": 4})
+    assert v and v[0].documentId == "d1"
+    hy = h.search(q, {"topK": 4})
+    want = reciprocal_rank_fusion(fts.search(q, {"limit": 8}), h.vector_store.search(q, {"topK": 8}), 4)
+    assert [(r.id, r.score) for r in hy] == [(r.id, r.score) for r in want]
+    assert h.search("a b", {"mode": "fts"}) == []            # terms of length <= 2 are dropped (sqlite.ts:139-147)
+    by_type = h.search_by_type(q, {"topK": 6})
+    assert set(by_type) == {"runbooks", "postmortems", "architecture", "knownIssues"}
+    h.close()
+    embedder.reset()
