@@ -122,6 +122,15 @@ rbk_status rbk_merge_topk_device(int32_t device, void* cuda_stream, int32_t G, i
                                  const void* dev_slots_i64, const void* dev_scores_f64, const void* dev_counts_i32,
                                  void* dev_out_slots_i64, void* dev_out_scores_f64, void* dev_out_counts_i32);
 
+/* Same merge for G PACKED per-shard blocks laid end to end (what ONE all-gather of each rank's block
+ * produces).  Block layout, rbk_packed_block_bytes(B, k_fetch) bytes: slots i64[B*k_fetch] | scores
+ * f64[B*k_fetch] | counts i32[B] (padded to 16 bytes).  rbk_index_search_device can write straight into a
+ * block: pass block, block + B*k_fetch*8 and block + B*k_fetch*16 as its three output pointers. */
+int64_t rbk_packed_block_bytes(int32_t B, int32_t k_fetch);
+rbk_status rbk_merge_topk_packed_device(int32_t device, void* cuda_stream, int32_t G, int32_t B, int32_t k_fetch,
+                                        const void* dev_blocks, void* dev_out_slots_i64, void* dev_out_scores_f64,
+                                        void* dev_out_counts_i32);
+
 /* ---- introspection ---- */
 typedef struct {
   int64_t searches;         /* search calls */

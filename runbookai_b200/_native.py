@@ -21,7 +21,8 @@ SYMBOLS = [
     "rbk_index_set_slot_base", "rbk_index_append_f64", "rbk_index_append_f32", "rbk_index_append_bf16",
     "rbk_index_append_bf16_device", "rbk_index_overwrite_f64", "rbk_index_tombstone", "rbk_index_clear",
     "rbk_index_count", "rbk_index_size", "rbk_index_dim", "rbk_index_read_rows_bf16", "rbk_index_search_f64",
-    "rbk_index_search_f32", "rbk_index_search_device", "rbk_merge_topk_device", "rbk_index_stats",
+    "rbk_index_search_f32", "rbk_index_search_device", "rbk_merge_topk_device", "rbk_packed_block_bytes",
+    "rbk_merge_topk_packed_device", "rbk_index_stats",
     "rbk_index_debug_scores_f32",
 ]
 
@@ -74,6 +75,9 @@ def _load() -> C.CDLL:
         getattr(lib, n).argtypes = [vp, vp, i32, i32, i32, f64, vp, vp, vp, C.POINTER(C.c_float)]
     lib.rbk_index_search_device.argtypes = [vp, vp, i32, i32, f64, vp, vp, vp]
     lib.rbk_merge_topk_device.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.rbk_packed_block_bytes.argtypes = [i32, i32]
+    lib.rbk_packed_block_bytes.restype = i64
+    lib.rbk_merge_topk_packed_device.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp, vp]
     lib.rbk_index_stats.argtypes = [vp, C.POINTER(RbkStats)]
     lib.rbk_index_debug_scores_f32.argtypes = [vp, vp, i32, vp]
     return lib
@@ -216,3 +220,14 @@ def merge_topk_device(device: int, stream: int, G: int, B: int, k_fetch: int, sl
     check(lib.rbk_merge_topk_device(device, C.c_void_p(stream), G, B, k_fetch, C.c_void_p(slots_ptr),
                                     C.c_void_p(scores_ptr), C.c_void_p(counts_ptr), C.c_void_p(out_slots_ptr),
                                     C.c_void_p(out_scores_ptr), C.c_void_p(out_counts_ptr)))
+
+
+def packed_block_bytes(B: int, k_fetch: int) -> int:
+    return lib.rbk_packed_block_bytes(B, k_fetch)
+
+
+def merge_topk_packed_device(device: int, stream: int, G: int, B: int, k_fetch: int, blocks_ptr: int,
+                             out_slots_ptr: int, out_scores_ptr: int, out_counts_ptr: int) -> None:
+    check(lib.rbk_merge_topk_packed_device(device, C.c_void_p(stream), G, B, k_fetch, C.c_void_p(blocks_ptr),
+                                           C.c_void_p(out_slots_ptr), C.c_void_p(out_scores_ptr),
+                                           C.c_void_p(out_counts_ptr)))

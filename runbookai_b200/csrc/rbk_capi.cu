@@ -758,8 +758,30 @@ rbk_status rbk_merge_topk_device(int32_t device, void* cuda_stream, int32_t G, i
   if (!dev_slots || !dev_scores || !dev_counts || !dev_out_slots || !dev_out_scores || !dev_out_counts)
     return fail(RBK_EINVAL, "null device pointer");
   DeviceGuard dg(device);
-  CK(launch_merge_shards(G, B, k_fetch, static_cast<const long long*>(dev_slots),
-                         static_cast<const double*>(dev_scores), static_cast<const int*>(dev_counts),
+  const size_t nk = static_cast<size_t>(B) * k_fetch;
+  CK(launch_merge_shards(G, B, k_fetch, dev_slots, dev_scores, dev_counts, nk * 8, nk * 8, static_cast<size_t>(B) * 4,
+                         static_cast<long long*>(dev_out_slots), static_cast<double*>(dev_out_scores),
+                         static_cast<int*>(dev_out_counts), static_cast<cudaStream_t>(cuda_stream)));
+  return RBK_OK;
+}
+
+int64_t rbk_packed_block_bytes(int32_t B, int32_t k_fetch) {
+  const int64_t nk = static_cast<int64_t>(B) * k_fetch;
+  return nk * 16 + ((static_cast<int64_t>(B) * 4 + 15) / 16) * 16;
+}
+
+rbk_status rbk_merge_topk_packed_device(int32_t device, void* cuda_stream, int32_t G, int32_t B, int32_t k_fetch,
+                                        const void* dev_blocks, void* dev_out_slots, void* dev_out_scores,
+                                        void* dev_out_counts) {
+  if (G < 1 || B < 0 || k_fetch < 1) return fail(RBK_EINVAL, "bad merge shape");
+  if (B == 0) return RBK_OK;
+  if (!dev_blocks || !dev_out_slots || !dev_out_scores || !dev_out_counts)
+    return fail(RBK_EINVAL, "null device pointer");
+  DeviceGuard dg(device);
+  const size_t nk = static_cast<size_t>(B) * k_fetch;
+  const size_t stride = static_cast<size_t>(rbk_packed_block_bytes(B, k_fetch));
+  const char* base = static_cast<const char*>(dev_blocks);
+  CK(launch_merge_shards(G, B, k_fetch, base, base + nk * 8, base + nk * 16, stride, stride, stride,
                          static_cast<long long*>(dev_out_slots), static_cast<double*>(dev_out_scores),
                          static_cast<int*>(dev_out_counts), static_cast<cudaStream_t>(cuda_stream)));
   return RBK_OK;

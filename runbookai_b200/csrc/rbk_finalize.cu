@@ -124,10 +124,20 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const SrcT* __restric
 // --------------------------------------------------------------------------- finalize
 constexpr int kFinThreads = 256;
 
-// Visit every candidate key of one query: lists (qb, r, qrow) for r in [0, R).
+constexpr int kQChunk = 512;    // query elements staged per re-rank chunk
+// Candidate keys of one query are staged in dynamic smem (key_cap keys, chosen per launch: large for few
+// queries, small for many so that 8 blocks fit an SM); a query with more keys streams them from L2.
+
+// Visit every candidate key of one query: from the smem staging buffer when it holds them all,
+// else straight from the per-unit lists (qb, r, qrow), r in [0, R), in L2.
 template <typename F>
-__device__ __forceinline__ void for_each_key(const unsigned long long* __restrict__ cand, const int* s_cnt, int QB, int R,
-                                             int qb, int qrow, int block_m, F&& f) {
+__device__ __forceinline__ void for_each_key(const unsigned long long* __restrict__ cand, const int* s_cnt,
+                                             const unsigned long long* s_keys, int M, bool staged, int R, int qb,
+                                             int qrow, int block_m, F&& f) {
+  if (staged) {
+    for (int i = threadIdx.x; i < M; i += kFinThreads) f(s_keys[i]);
+    return;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int r = warp; r < R; r += kFinThreads / 32) {
     const unsigned long long* l =
@@ -135,7 +145,6 @@ __device__ __forceinline__ void for_each_key(const unsigned long long* __restric
     const int c = s_cnt[r];
     for (int i = lane; i < c; i += 32) f(__ldcg(l + i));
   }
-  (void)QB;
 }
 
 __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p) {
@@ -144,6 +153,8 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p)
   const int qb = ql / p.block_m, qrow = ql % p.block_m;
 
   __shared__ int s_cnt[160];
+  __shared__ int s_off[161];
+  extern __shared__ __align__(16) unsigned long long s_keys[];   // p.key_cap keys; later the re-rank's row chunks
   __shared__ unsigned int s_hist[256];
   __shared__ unsigned long long s_sel[kMaxKPrime];
   __shared__ double s_score[kMaxKPrime];
@@ -170,6 +181,47 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p)
   __syncthreads();
   const int M = s_total;
   const int kprime = p.kprime;
+  // Stage the query's keys in smem with every load in flight at once: flat key index ->
+  // (list, offset) by binary search in the prefix sums.  (Walking the lists one after the
+  // other costs one L2 round trip per list and pass: 60-125 us per block, measured.)
+  const bool staged = M <= p.key_cap;
+  if (staged) {
+    if (tid < 32) {   // exclusive scan of up to 160 counts, 5 per lane
+      int v[5], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const int r = tid * 5 + j;
+        v[j] = r < p.R ? s_cnt[r] : 0;
+        sum += v[j];
+      }
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, incl, o);
+        if (tid >= o) incl += t;
+      }
+      int run = incl - sum;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const int r = tid * 5 + j;
+        if (r <= p.R) s_off[r] = run;
+        run += v[j];
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < M; i += kFinThreads) {
+      int lo = 0, hi = p.R - 1;   // last r with s_off[r] <= i
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_off[mid] <= i) lo = mid;
+        else hi = mid - 1;
+      }
+      const unsigned long long* l =
+          p.cand + (static_cast<size_t>(qb * p.R + lo) * p.block_m + qrow) * static_cast<size_t>(kListCap);
+      s_keys[i] = __ldcg(l + (i - s_off[lo]));
+    }
+    __syncthreads();
+  }
 
   // ---- K2: radix select of the k'-th largest 64-bit key (keys are unique) ----
   unsigned long long pivot = 0ull;
@@ -184,7 +236,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p)
       s_hist[tid] = 0u;
       __syncthreads();
       const unsigned long long prefix = s_prefix;
-      for_each_key(p.cand, s_cnt, p.QB, p.R, qb, qrow, p.block_m, [&](unsigned long long k) {
+      for_each_key(p.cand, s_cnt, s_keys, M, staged, p.R, qb, qrow, p.block_m, [&](unsigned long long k) {
         if ((k & mask) == prefix) atomicAdd(&s_hist[static_cast<unsigned>(k >> shift) & 255u], 1u);
       });
       __syncthreads();
@@ -221,7 +273,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p)
     }
     pivot = s_prefix;
   }
-  for_each_key(p.cand, s_cnt, p.QB, p.R, qb, qrow, p.block_m, [&](unsigned long long k) {
+  for_each_key(p.cand, s_cnt, s_keys, M, staged, p.R, qb, qrow, p.block_m, [&](unsigned long long k) {
     if (k >= pivot) {
       const int pos = atomicAdd(&s_nsel, 1);
       if (pos < kMaxKPrime) s_sel[pos] = k;
@@ -233,14 +285,53 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p)
   const float tau_raw = M >= kprime ? key_score(pivot) : -INFINITY;
 
   // ---- K4: exact fp64 re-score of the candidates ----
+  // The arithmetic is a sequential chain per candidate (parity contract), so global-load latency
+  // must not sit inside it: all threads stage a K-chunk of every candidate row (and of the query)
+  // into smem with the loads in flight together, then each candidate's thread walks its chunk.
+  // The key staging buffer is dead by now (selection is in s_sel) and is reused for the rows.
   const double na = p.q.q_norm2[ql];
   const double* qv = p.q.q_f64 + static_cast<size_t>(ql) * p.d;
+  __shared__ double s_q[kQChunk];
+  unsigned char* s_rows = reinterpret_cast<unsigned char*>(s_keys);
+  int chunk = nsel > 0 ? ((p.key_cap * 8 / nsel - 16) / 2) & ~7 : kQChunk;
+  chunk = chunk < kQChunk ? chunk : kQChunk;
+  const int chunk16 = chunk >> 3;                                   // 16-byte units per row chunk
+  const int row_stride = (chunk16 | 1) << 4;                        // odd number of 16-B units: conflict-free walks
+  int my_row = 0;
+  double dot = 0.0;
+  if (tid < nsel) my_row = static_cast<int>(key_row(s_sel[tid]));
+  for (int c0 = 0; c0 < p.d; c0 += chunk) {
+    const int len = p.d - c0 < chunk ? p.d - c0 : chunk;            // elements of this chunk
+    const int len16 = (len + 7) >> 3;                               // rows are zero padded to dpad (multiple of 8)
+    __syncthreads();                                                // previous chunk fully consumed
+    for (int i = tid; i < nsel * len16; i += kFinThreads) {
+      const int rr = i / len16, u = i - rr * len16;
+      const int row = static_cast<int>(key_row(s_sel[rr]));
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.rows + static_cast<size_t>(row) * p.dpad + c0) + u);
+      *reinterpret_cast<uint4*>(s_rows + rr * row_stride + u * 16) = v;
+    }
+    for (int i = tid; i < len; i += kFinThreads) s_q[i] = __ldg(qv + c0 + i);
+    __syncthreads();
+    if (tid < nsel) {
+      const unsigned char* mine = s_rows + tid * row_stride;
+      int i = 0;
+      for (; i + 8 <= len; i += 8) {
+        const uint4 v = *reinterpret_cast<const uint4*>(mine + i * 2);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dot = __dadd_rn(dot, __dmul_rn(s_q[i + 2 * j], bf16_to_f64(w[j] & 0xFFFFu)));
+          dot = __dadd_rn(dot, __dmul_rn(s_q[i + 2 * j + 1], bf16_to_f64(w[j] >> 16)));
+        }
+      }
+      for (; i < len; ++i)
+        dot = __dadd_rn(dot, __dmul_rn(s_q[i], bf16_to_f64(reinterpret_cast<const uint16_t*>(mine)[i])));
+    }
+  }
   if (tid < nsel) {
-    const int row = static_cast<int>(key_row(s_sel[tid]));
-    const double dot = exact_dot(qv, p.rows + static_cast<size_t>(row) * p.dpad, p.d);
-    const double sc = exact_cosine(dot, na, p.row_norm2[row]);
+    const double sc = exact_cosine(dot, na, p.row_norm2[my_row]);
     s_score[tid] = sc;
-    s_row[tid] = row;
+    s_row[tid] = my_row;
     const int ok = sc >= p.min_score ? 1 : 0;  // vector-store.ts:212 (NaN fails; -inf = no threshold)
     s_valid[tid] = ok;
     if (ok) atomicAdd(&s_nvalid, 1);
@@ -429,37 +520,44 @@ __global__ void __launch_bounds__(kExThreads) exact_merge_kernel(ExactParams p) 
 // Lists are sorted by (score desc, slot asc); slots are globally unique, so the rank of an
 // entry in the merged order is its own index plus, for every other list, the number of
 // entries of that list that come before it (binary search).
-__global__ void __launch_bounds__(128) merge_shards_kernel(int G, int B, int k, const long long* __restrict__ slots,
-                                                           const double* __restrict__ scores,
-                                                           const int* __restrict__ counts, long long* out_slots,
-                                                           double* out_scores, int* out_counts) {
+__global__ void __launch_bounds__(128) merge_shards_kernel(int G, int B, int k, const char* __restrict__ slots_base,
+                                                           const char* __restrict__ scores_base,
+                                                           const char* __restrict__ counts_base, size_t slots_stride,
+                                                           size_t scores_stride, size_t counts_stride,
+                                                           long long* out_slots, double* out_scores, int* out_counts) {
+  // shard g's arrays start g * stride bytes after shard 0's (dense [G][...] arrays: stride = array size;
+  // packed per-rank blocks, e.g. straight out of ONE all-gather: the same block stride for all three)
+  auto slots_of = [&](int g) { return reinterpret_cast<const long long*>(slots_base + g * slots_stride); };
+  auto scores_of = [&](int g) { return reinterpret_cast<const double*>(scores_base + g * scores_stride); };
+  auto count_of = [&](int g, int b) { return reinterpret_cast<const int*>(counts_base + g * counts_stride)[b]; };
   const int b = blockIdx.x;
   int total = 0;
-  for (int g = 0; g < G; ++g) total += counts[g * B + b];
+  for (int g = 0; g < G; ++g) total += count_of(g, b);
   const int n_out = total < k ? total : k;
   for (int i = threadIdx.x; i < G * k; i += blockDim.x) {
     const int g = i / k, e = i % k;
-    if (e >= counts[g * B + b]) continue;
-    const size_t o = (static_cast<size_t>(g) * B + b) * k;
-    const double sc = scores[o + e];
-    const long long sl = slots[o + e];
+    if (e >= count_of(g, b)) continue;
+    const size_t o = static_cast<size_t>(b) * k;
+    const double sc = scores_of(g)[o + e];
+    const long long sl = slots_of(g)[o + e];
     int rank = e;
     for (int g2 = 0; g2 < G; ++g2) {
       if (g2 == g) continue;
-      const size_t o2 = (static_cast<size_t>(g2) * B + b) * k;
-      int lo = 0, hi = counts[g2 * B + b];
+      const double* s2p = scores_of(g2) + o;
+      const long long* l2p = slots_of(g2) + o;
+      int lo = 0, hi = count_of(g2, b);
       while (lo < hi) {  // first index whose entry does NOT come before (sc, sl)
         const int mid = (lo + hi) >> 1;
-        const double s2 = scores[o2 + mid];
-        const long long l2 = slots[o2 + mid];
+        const double s2 = s2p[mid];
+        const long long l2 = l2p[mid];
         if (s2 > sc || (s2 == sc && l2 < sl)) lo = mid + 1;
         else hi = mid;
       }
       rank += lo;
     }
     if (rank < k) {
-      out_slots[static_cast<size_t>(b) * k + rank] = sl;
-      out_scores[static_cast<size_t>(b) * k + rank] = sc;
+      out_slots[o + rank] = sl;
+      out_scores[o + rank] = sc;
     }
   }
   for (int i = n_out + threadIdx.x; i < k; i += blockDim.x) {
@@ -482,9 +580,15 @@ cudaError_t launch_prep_queries(const void* src, int src_type, int B, int d, int
   return cudaGetLastError();
 }
 
-cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t stream) {
-  if (p.B <= 0) return cudaSuccess;
-  finalize_kernel<<<p.B, kFinThreads, 0, stream>>>(p);
+cudaError_t launch_finalize(const FinalizeParams& p_in, cudaStream_t stream) {
+  if (p_in.B <= 0) return cudaSuccess;
+  FinalizeParams p = p_in;
+  // >= 2048 keys (16 KB: room for 128 candidate rows x 56 elements per re-rank chunk)
+  p.key_cap = p.B <= 160 ? 16384 : (p.B <= 320 ? 8192 : 2048);
+  const size_t smem = static_cast<size_t>(p.key_cap) * 8;
+  cudaError_t e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+  if (e != cudaSuccess) return e;
+  finalize_kernel<<<p.B, kFinThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -498,11 +602,14 @@ cudaError_t launch_exact_fallback(const ExactParams& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_merge_shards(int G, int B, int k_fetch, const long long* slots, const double* scores,
-                                const int* counts, long long* out_slots, double* out_scores, int* out_counts,
-                                cudaStream_t stream) {
+cudaError_t launch_merge_shards(int G, int B, int k_fetch, const void* slots, const void* scores, const void* counts,
+                                size_t slots_stride, size_t scores_stride, size_t counts_stride, long long* out_slots,
+                                double* out_scores, int* out_counts, cudaStream_t stream) {
   if (B <= 0) return cudaSuccess;
-  merge_shards_kernel<<<B, 128, 0, stream>>>(G, B, k_fetch, slots, scores, counts, out_slots, out_scores, out_counts);
+  merge_shards_kernel<<<B, 128, 0, stream>>>(G, B, k_fetch, static_cast<const char*>(slots),
+                                             static_cast<const char*>(scores), static_cast<const char*>(counts),
+                                             slots_stride, scores_stride, counts_stride, out_slots, out_scores,
+                                             out_counts);
   return cudaGetLastError();
 }
 

@@ -77,6 +77,7 @@ struct FinalizeParams {
   const int* cand_cnt;
   int QB, R, kprime, k_fetch, B, d, dpad;
   int block_m;  // queries per list block: 128 (1-CTA scan) or 256 (CTA-pair scan)
+  int key_cap;  // keys staged in smem per query (set by launch_finalize)
   int q0;  // global index of the first query of this launch (sub-batch offset)
   double min_score;
   const uint16_t* rows;
@@ -113,9 +114,10 @@ struct ExactParams {
 };
 cudaError_t launch_exact_fallback(const ExactParams& p, cudaStream_t stream);
 
-cudaError_t launch_merge_shards(int G, int B, int k_fetch, const long long* slots, const double* scores,
-                                const int* counts, long long* out_slots, double* out_scores, int* out_counts,
-                                cudaStream_t stream);
+// slots/scores/counts point at shard 0's arrays; shard g's arrays start g * <stride> bytes later.
+cudaError_t launch_merge_shards(int G, int B, int k_fetch, const void* slots, const void* scores, const void* counts,
+                                size_t slots_stride, size_t scores_stride, size_t counts_stride, long long* out_slots,
+                                double* out_scores, int* out_counts, cudaStream_t stream);
 
 // Bound on the fp32 tensor-core accumulation + scaling error of an approximate cosine.
 inline double accumulation_eps(int d) { return (double)(d + 8) * (1.0 / 4194304.0); }  // (d+8) * 2^-22

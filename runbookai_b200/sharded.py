@@ -54,46 +54,53 @@ class ShardedSearcher:
         self._bufs: dict = {}
 
     def _buffers(self, B: int, k: int, device):
+        """One PACKED block per rank (slots i64 | scores f64 | counts i32, include/rbk_knn.h) so the
+        exchange is a single all-gather; the local search writes straight into this rank's block."""
         key = (B, k, str(device))
         if key not in self._bufs:
             G = self.world
-            self._bufs = {key: dict(
-                ls=torch.empty((B, k), dtype=torch.int64, device=device),
-                lv=torch.empty((B, k), dtype=torch.float64, device=device),
-                lc=torch.empty((B,), dtype=torch.int32, device=device),
-                gs=torch.empty((G, B, k), dtype=torch.int64, device=device),
-                gv=torch.empty((G, B, k), dtype=torch.float64, device=device),
-                gc=torch.empty((G, B), dtype=torch.int32, device=device),
-                os=torch.empty((B, k), dtype=torch.int64, device=device),
-                ov=torch.empty((B, k), dtype=torch.float64, device=device),
-                oc=torch.empty((B,), dtype=torch.int32, device=device))}
+            nk = B * k
+            blk = _native.packed_block_bytes(B, k) if device.type == "cuda" else nk * 16 + -(-B * 4 // 16) * 16
+            local = torch.empty((blk,), dtype=torch.uint8, device=device)
+            allb = torch.empty((G * blk,), dtype=torch.uint8, device=device)
+
+            def views(buf, off):
+                return (buf[off:off + nk * 8].view(torch.int64).view(B, k),
+                        buf[off + nk * 8:off + nk * 16].view(torch.float64).view(B, k),
+                        buf[off + nk * 16:off + nk * 16 + B * 4].view(torch.int32))
+            self._bufs = {key: dict(blk=blk, local=local, all=allb, l=views(local, 0),
+                                    g=[views(allb, g * blk) for g in range(G)],
+                                    os=torch.empty((B, k), dtype=torch.int64, device=device),
+                                    ov=torch.empty((B, k), dtype=torch.float64, device=device),
+                                    oc=torch.empty((B,), dtype=torch.int32, device=device))}
         return self._bufs[key]
 
     def search_device(self, q_dev: torch.Tensor, k_fetch: int, min_score: float | None):
         """q_dev: float32 [B, d] on this rank's GPU.  Returns device (slots, scores, counts)."""
         B = q_dev.shape[0]
         buf = self._buffers(B, k_fetch, q_dev.device)
+        ls, lv, lc = buf["l"]
         if self._local_search is not None:      # CPU test hook
-            ls, lv, lc = self._local_search(q_dev, k_fetch, min_score)
-            buf["ls"].copy_(ls), buf["lv"].copy_(lv), buf["lc"].copy_(lc)
+            s, v, c = self._local_search(q_dev, k_fetch, min_score)
+            ls.copy_(s), lv.copy_(v), lc.copy_(c)
         else:
-            self.index.search_device(q_dev.data_ptr(), B, k_fetch, min_score, buf["ls"].data_ptr(),
-                                     buf["lv"].data_ptr(), buf["lc"].data_ptr())
+            self.index.search_device(q_dev.data_ptr(), B, k_fetch, min_score, ls.data_ptr(), lv.data_ptr(),
+                                     lc.data_ptr())
         if self.world == 1:
-            return buf["ls"], buf["lv"], buf["lc"]
-        # the single exchange step of the path: per-rank top-k lists, <= B*k*20 bytes per rank
-        G = self.world   # outputs viewed as the concatenation along dim 0 (what gloo insists on)
-        dist.all_gather_into_tensor(buf["gs"].view(G * B, k_fetch), buf["ls"], group=self.group)
-        dist.all_gather_into_tensor(buf["gv"].view(G * B, k_fetch), buf["lv"], group=self.group)
-        dist.all_gather_into_tensor(buf["gc"].view(G * B), buf["lc"], group=self.group)
-        if self._merge is not None:
-            s, v, c = self._merge(buf["gs"], buf["gv"], buf["gc"], k_fetch)
+            return ls, lv, lc
+        # the single exchange step of the path: one all-gather of <= B*(k*16+4) bytes per rank
+        dist.all_gather_into_tensor(buf["all"], buf["local"], group=self.group)
+        if self._merge is not None:             # CPU test hook
+            gs = torch.stack([g[0] for g in buf["g"]])
+            gv = torch.stack([g[1] for g in buf["g"]])
+            gc = torch.stack([g[2] for g in buf["g"]])
+            s, v, c = self._merge(gs, gv, gc, k_fetch)
             buf["os"].copy_(s), buf["ov"].copy_(v), buf["oc"].copy_(c)
         else:
             stream = torch.cuda.current_stream(q_dev.device).cuda_stream
-            _native.merge_topk_device(q_dev.device.index or 0, stream, self.world, B, k_fetch,
-                                      buf["gs"].data_ptr(), buf["gv"].data_ptr(), buf["gc"].data_ptr(),
-                                      buf["os"].data_ptr(), buf["ov"].data_ptr(), buf["oc"].data_ptr())
+            _native.merge_topk_packed_device(q_dev.device.index or 0, stream, self.world, B, k_fetch,
+                                             buf["all"].data_ptr(), buf["os"].data_ptr(), buf["ov"].data_ptr(),
+                                             buf["oc"].data_ptr())
         return buf["os"], buf["ov"], buf["oc"]
 
     def search(self, queries_host: torch.Tensor, k_fetch: int, min_score: float | None, device):

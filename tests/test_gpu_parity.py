@@ -268,6 +268,19 @@ def test_logical_shards_and_merge_kernel(rb, oracle_mod, native):
     es, ev, ec = oracle_mod.search_batch_mt(corpus, q.astype(np.float64), k, None)
     assert (oc.cpu().numpy() == ec).all()
     assert (os_.cpu().numpy() == es).all() and (ov.cpu().numpy() == ev).all()
+    # the packed variant (one block per shard, what a single all-gather produces)
+    blk = native.packed_block_bytes(b, k)
+    packed = torch.zeros((G * blk,), dtype=torch.uint8, device=dev)
+    for g in range(G):
+        o = g * blk
+        packed[o:o + b * k * 8].view(torch.int64).copy_(gs[g].reshape(-1))
+        packed[o + b * k * 8:o + b * k * 16].view(torch.float64).copy_(gv[g].reshape(-1))
+        packed[o + b * k * 16:o + b * k * 16 + b * 4].view(torch.int32).copy_(gc[g])
+    os2, ov2, oc2 = torch.empty_like(os_), torch.empty_like(ov), torch.empty_like(oc)
+    native.merge_topk_packed_device(0, torch.cuda.current_stream().cuda_stream, G, b, k, packed.data_ptr(),
+                                    os2.data_ptr(), ov2.data_ptr(), oc2.data_ptr())
+    torch.cuda.synchronize()
+    assert (os2 == os_).all() and (ov2 == ov).all() and (oc2 == oc).all()
     for ix in shards:
         ix.close()
 
