@@ -13,7 +13,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "lib" / "librbk_knn.so"
-SOURCES = ["rbk_capi.cu", "rbk_scan.cu", "rbk_scan2.cu", "rbk_ingest.cu", "rbk_finalize.cu"]
+SOURCES = ["rbk_capi.cu", "rbk_scan.cu", "rbk_scan2.cu", "rbk_scan3.cu", "rbk_ingest.cu", "rbk_finalize.cu"]
 HEADERS = ["rbk_internal.h", "rbk_ptx.cuh", "rbk_epilogue.cuh", "../../include/rbk_knn.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

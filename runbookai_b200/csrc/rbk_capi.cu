@@ -149,7 +149,8 @@ struct rbk_index {
   PinBuf<long long> h_slots;
   PinBuf<double> h_scores;
   PinBuf<float> h_f32;
-  CUtensorMap tmap_c, tmap_c_half, tmap_c_half32, tmap_c_pf;
+  CUtensorMap tmap_c, tmap_c_half, tmap_c_half32, tmap_c_pf, tmap_c_r32;
+  bool use_ts = false;  // pair kernel with queries in TMEM (dim <= 768): correct but not yet faster
   bool force_1cta = false, force_streamed = true;   // query-resident pair kernel: measured slower
   int prefetch_tiles = 0;
   const void* tmap_c_base = nullptr;
@@ -282,6 +283,8 @@ rbk_status refresh_corpus_tmap(rbk_index* ix) {
   if (st != RBK_OK) return st;
   st = encode_rows_tmap(&ix->tmap_c_pf, ix->rows, ix->n_rows, ix->dpad, kBlockN / 2, 256);
   if (st != RBK_OK) return st;
+  st = encode_rows_tmap(&ix->tmap_c_r32, ix->rows, ix->n_rows, ix->dpad, 32);
+  if (st != RBK_OK) return st;
   ix->tmap_c_base = ix->rows;
   ix->tmap_c_rows = ix->n_rows;
   return RBK_OK;
@@ -370,7 +373,10 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
     CK(cudaEventRecord(get_event(ix, (*ev_cursor)++), ix->stream));
     const bool resident = pairs && !ix->force_streamed && scan2_resident_fits(ix->dpad);
     sp.prefetch_tiles = ix->prefetch_tiles;
-    if (pairs)
+    const bool ts = pairs && ix->use_ts && scan3_fits(ix->dpad);
+    if (ts)
+      CK(launch_scan3(ix->tmap_c_r32, sp, ix->q_bf16.p + static_cast<size_t>(q0) * ix->dpad, ix->stream));
+    else if (pairs)
       CK(launch_scan2(tmap_q, (resident && scan2_resident_k() == 32) ? ix->tmap_c_half32 : ix->tmap_c_half,
                       ix->tmap_c_pf, sp, resident, ix->stream));
     else CK(launch_scan(tmap_q, ix->tmap_c, sp, ix->stream));
@@ -561,6 +567,7 @@ rbk_status rbk_index_create(int32_t dim, int32_t device, int64_t capacity_hint, 
   if (const char* m = getenv("RBK_KNN_MARGIN")) ix->margin = std::max(0, std::min(96, atoi(m)));
   if (const char* m = getenv("RBK_KNN_FORCE_1CTA")) ix->force_1cta = atoi(m) != 0;   // A/B measurements only
   if (const char* m = getenv("RBK_KNN_RESIDENT")) ix->force_streamed = atoi(m) == 0;   // experiments only
+  if (const char* m = getenv("RBK_KNN_TS")) ix->use_ts = atoi(m) != 0;
   if (const char* m = getenv("RBK_KNN_PREFETCH_TILES")) ix->prefetch_tiles = std::max(0, std::min(64, atoi(m)));
   e = cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {

@@ -228,12 +228,22 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
               p.hist + static_cast<size_t>(q_valid ? q : 0) * kHistBins, p.maxbin + (q_valid ? q : 0));
   int as = 0;
   uint32_t aph = 0;
+  // the next tile's 1/||c|| travels in registers while this tile is processed (hides its L2/HBM latency)
+  float nx0 = 0.f, nx1 = 0.f;
+  if (t0 < t1) {
+    nx0 = __ldg(p.inv_norm_c + t0 * kBlockN + et);
+    nx1 = __ldg(p.inv_norm_c + t0 * kBlockN + kEpi + et);
+  }
   for (int tile = t0; tile < t1; ++tile) {
     const int row0 = tile * kBlockN;
     const int it = tile - t0;
     float* invc = invc_stage[as];
-    invc[et] = __ldg(p.inv_norm_c + row0 + et);
-    invc[kEpi + et] = __ldg(p.inv_norm_c + row0 + kEpi + et);
+    invc[et] = nx0;
+    invc[kEpi + et] = nx1;
+    if (tile + 1 < t1) {
+      nx0 = __ldg(p.inv_norm_c + (tile + 1) * kBlockN + et);
+      nx1 = __ldg(p.inv_norm_c + (tile + 1) * kBlockN + kEpi + et);
+    }
     named_bar_sync(1, kEpi);
     if (it != 0 && (it < 8 || (it & 3) == 0)) filter_refresh(fs, p.kprime);   // overlaps this tile's MMAs
     mbar_wait(smem_u32(&tmem_full[as]), aph);

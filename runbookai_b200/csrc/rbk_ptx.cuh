@@ -203,6 +203,21 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
       : "memory");
 }
 
+// One lane of a converged warp.  The producer and MMA roles run their loops with the WHOLE warp
+// (uniform control flow, operands in uniform registers) and elect a lane only around the
+// asynchronous instruction itself: a loop that lives inside `if (lane == 0)` makes every operand
+// a per-thread value and costs an ELECT + R2UR round trip per descriptor (~16 instructions per
+// tcgen05.mma, seen in the ncu source view), which made 32-cycle N=64 MMAs issue-bound.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

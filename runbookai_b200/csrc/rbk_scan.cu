@@ -77,52 +77,54 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
   const uint32_t tmem_base = tail->tmem_base;
 
   if (warp == 0) {
-    // ===================== TMA producer (one thread) =====================
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      volatile int* prog = p.progress + r * p.QB;
-      for (int tile = t0; tile < t1; ++tile) {
-        lockstep_pace(prog, p.QB, qb, tile - t0);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
-          const uint32_t full = smem_u32(&tail->full[s]);
+    // ===================== TMA producer (whole warp, elected issue) =====================
+    volatile int* prog = p.progress + r * p.QB;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = t0; tile < t1; ++tile) {
+      if (lane == 0) lockstep_pace(prog, p.QB, qb, tile - t0);
+      __syncwarp();
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
+        const uint32_t full = smem_u32(&tail->full[s]);
+        const uint32_t a_dst = smem_base + s * kStageBytes;
+        if (elect_one()) {
           mbar_arrive_expect_tx(full, kStageBytes);
-          const uint32_t a_dst = smem_base + s * kStageBytes;
           tma_load_2d(a_dst, &tmap_q, full, kb * kBlockK, qb * kBlockM);
           tma_load_2d(a_dst + kABytes, &tmap_c, full, kb * kBlockK, tile * kBlockN);
-          if (++s == kStages) { s = 0; ph ^= 1u; }
         }
+        __syncwarp();
+        if (++s == kStages) { s = 0; ph ^= 1u; }
       }
-      if (p.QB > 1) prog[qb] = 0x7FFFFFFF;  // done: never hold a peer back
     }
+    if (lane == 0 && p.QB > 1) prog[qb] = 0x7FFFFFFF;  // done: never hold a peer back
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(kBlockM, kBlockN);
-      int s = 0, as = 0;
-      uint32_t ph = 0, aph = 0;
-      for (int tile = t0; tile < t1; ++tile) {
-        mbar_wait(smem_u32(&tail->tmem_empty[as]), aph ^ 1u);
+    // ===================== MMA issuer (whole warp, elected issue) =====================
+    constexpr uint32_t idesc = make_idesc_bf16_f32(kBlockM, kBlockN);
+    int s = 0, as = 0;
+    uint32_t ph = 0, aph = 0;
+    for (int tile = t0; tile < t1; ++tile) {
+      mbar_wait(smem_u32(&tail->tmem_empty[as]), aph ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * kBlockN);
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(smem_u32(&tail->full[s]), ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * kBlockN);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(smem_u32(&tail->full[s]), ph);
-          tc_fence_after();
-          const uint32_t a0 = smem_base + s * kStageBytes;
-          const uint32_t b0 = a0 + kABytes;
+        const uint64_t adesc0 = make_sw128_kmajor_desc(smem_base + s * kStageBytes);
+        const uint64_t bdesc0 = make_sw128_kmajor_desc(smem_base + s * kStageBytes + kABytes);
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            umma_bf16_ss(d_tmem, make_sw128_kmajor_desc(a0 + k * 32), make_sw128_kmajor_desc(b0 + k * 32), idesc,
+          for (int k = 0; k < kBlockK / 16; ++k)   // +32 bytes per k-step = +2 in the 16-byte address field
+            umma_bf16_ss(d_tmem, adesc0 + static_cast<uint64_t>(2 * k), bdesc0 + static_cast<uint64_t>(2 * k), idesc,
                          (kb | k) != 0 ? 1u : 0u);
-          }
           umma_commit(smem_u32(&tail->empty[s]));  // smem slot reusable once these MMAs retire
           if (kb == p.num_kb - 1) umma_commit(smem_u32(&tail->tmem_full[as]));
-          if (++s == kStages) { s = 0; ph ^= 1u; }
         }
-        as ^= 1;
-        if (as == 0) aph ^= 1u;
+        __syncwarp();
+        if (++s == kStages) { s = 0; ph ^= 1u; }
       }
+      as ^= 1;
+      if (as == 0) aph ^= 1u;
     }
   } else {
     // ===================== epilogue: thread <-> query =====================

@@ -120,48 +120,53 @@ scan2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
   const uint32_t tmem_base = tail->tmem_base;
 
   if (warp == 0) {
-    // ===================== TMA producer (one thread per CTA) =====================
-    if (lane == 0) {
-      if (kRes) {
-        // this CTA's 128 queries, all K, once: 128-byte-swizzled panels of 64 columns
-        const uint32_t a_full = smem_u32(&tail->a_full);
+    // ===================== TMA producer (whole warp, elected issue; both CTAs) =====================
+    if (kRes) {
+      // this CTA's 128 queries, all K, once: 128-byte-swizzled panels of 64 columns
+      const uint32_t a_full = smem_u32(&tail->a_full);
+      if (elect_one()) {
         if (rank == 0) mbar_arrive_expect_tx(a_full, 2u * static_cast<uint32_t>(p.num_kb) * kPanelBytes);
         for (int kb = 0; kb < p.num_kb; ++kb)
           tma_load_2d_2cta(smem_base + kb * kPanelBytes, &tmap_q, a_full, kb * kBlockK, q_row0);
       }
-      volatile int* prog = p.progress + r * p.QB;
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = t0; tile < t1; ++tile) {
-        if (rank == 0) lockstep_pace(prog, p.QB, qb, tile - t0);
-        const int c_row0 = tile * kBlockN + static_cast<int>(rank) * kHalfN;
-        if (kRes && p.prefetch_tiles > 0 && tile + p.prefetch_tiles < t1) {
-          // the resident layout leaves only 32 KB of smem ring per CTA: fetch this CTA's rows of a
-          // later tile into L2 now so the ring's loads are L2 hits (prefetch boxes: 128 rows x 256 cols)
-          for (int c = 0; c < p.dpad; c += 256) tma_prefetch_l2_2d(&tmap_pf, c, c_row0 + p.prefetch_tiles * kBlockN);
-        }
-        for (int ks = 0; ks < n_ksteps; ++ks) {
-          mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
-          const uint32_t full = smem_u32(&tail->full[s]);
+      __syncwarp();
+    }
+    volatile int* prog = p.progress + r * p.QB;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = t0; tile < t1; ++tile) {
+      if (rank == 0 && lane == 0) lockstep_pace(prog, p.QB, qb, tile - t0);
+      __syncwarp();
+      const int c_row0 = tile * kBlockN + static_cast<int>(rank) * kHalfN;
+      if (kRes && p.prefetch_tiles > 0 && tile + p.prefetch_tiles < t1 && lane == 0) {
+        // the resident layout leaves only 32 KB of smem ring per CTA: fetch this CTA's rows of a
+        // later tile into L2 now so the ring's loads are L2 hits (prefetch boxes: 128 rows x 256 cols)
+        for (int c = 0; c < p.dpad; c += 256) tma_prefetch_l2_2d(&tmap_pf, c, c_row0 + p.prefetch_tiles * kBlockN);
+      }
+      for (int ks = 0; ks < n_ksteps; ++ks) {
+        mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
+        const uint32_t full = smem_u32(&tail->full[s]);
+        const uint32_t dst = ring_base + s * kStageBytes;
+        if (elect_one()) {
           // Only the leader arrives (once, expecting BOTH CTAs' bytes).  The peer's bytes may land
           // first and drive the tx-count negative; the phase cannot complete before the leader's
           // arrive, and the peer re-uses a slot only after the leader's MMAs consumed it.
           if (rank == 0) mbar_arrive_expect_tx(full, 2 * kStageBytes);
-          const uint32_t dst = ring_base + s * kStageBytes;
           if (kRes) {
             tma_load_2d_2cta(dst, &tmap_c, full, ks * kKR, c_row0);
           } else {
             tma_load_2d_2cta(dst, &tmap_q, full, ks * kBlockK, q_row0);
             tma_load_2d_2cta(dst + kPanelBytes, &tmap_c, full, ks * kBlockK, c_row0);
           }
-          if (++s == kStages) { s = 0; ph ^= 1u; }
         }
+        __syncwarp();
+        if (++s == kStages) { s = 0; ph ^= 1u; }
       }
-      if (rank == 0 && p.QB > 1) prog[qb] = 0x7FFFFFFF;   // done: never hold a peer back
     }
+    if (rank == 0 && lane == 0 && p.QB > 1) prog[qb] = 0x7FFFFFFF;   // done: never hold a peer back
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA, one thread) =====================
-    if (rank == 0 && lane == 0) {
+    // ===================== MMA issuer (leader CTA; whole warp, elected issue) =====================
+    if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16_f32(2 * kBlockM, kBlockN);
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
@@ -177,29 +182,34 @@ scan2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
           mbar_wait(smem_u32(&tail->full[s]), ph);
           tc_fence_after();
           const uint32_t st = ring_base + s * kStageBytes;
-          if (kRes) {
-            if constexpr (kKR == 32) {
-              // stage = 32 corpus columns; queries: panel ks/2, 64-byte half (ks&1) of its 128-byte rows
-              const uint32_t a0 = smem_base + (ks >> 1) * kPanelBytes + (ks & 1) * 64;
+          if (elect_one()) {
+            if (kRes) {
+              if constexpr (kKR == 32) {
+                // stage = 32 corpus columns; queries: panel ks/2, 64-byte half (ks&1) of its 128-byte rows
+                const uint32_t a0 = smem_base + (ks >> 1) * kPanelBytes + (ks & 1) * 64;
 #pragma unroll
-              for (int k = 0; k < kKR / 16; ++k)
-                umma_bf16_ss_2cta(d_tmem, make_sw128_kmajor_desc(a0 + k * 32), make_sw64_kmajor_desc(st + k * 32),
-                                  idesc, (ks | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < kKR / 16; ++k)
+                  umma_bf16_ss_2cta(d_tmem, make_sw128_kmajor_desc(a0 + k * 32), make_sw64_kmajor_desc(st + k * 32),
+                                    idesc, (ks | k) != 0 ? 1u : 0u);
+              } else {
+                const uint32_t a0 = smem_base + ks * kPanelBytes;
+#pragma unroll
+                for (int k = 0; k < kKR / 16; ++k)
+                  umma_bf16_ss_2cta(d_tmem, make_sw128_kmajor_desc(a0 + k * 32),
+                                    make_sw128_kmajor_desc(st + k * 32), idesc, (ks | k) != 0 ? 1u : 0u);
+              }
             } else {
-              const uint32_t a0 = smem_base + ks * kPanelBytes;
+              const uint64_t adesc0 = make_sw128_kmajor_desc(st);
+              const uint64_t bdesc0 = make_sw128_kmajor_desc(st + kPanelBytes);
 #pragma unroll
-              for (int k = 0; k < kKR / 16; ++k)
-                umma_bf16_ss_2cta(d_tmem, make_sw128_kmajor_desc(a0 + k * 32), make_sw128_kmajor_desc(st + k * 32),
+              for (int k = 0; k < kBlockK / 16; ++k)   // +32 bytes per k-step = +2 in the 16-byte address field
+                umma_bf16_ss_2cta(d_tmem, adesc0 + static_cast<uint64_t>(2 * k), bdesc0 + static_cast<uint64_t>(2 * k),
                                   idesc, (ks | k) != 0 ? 1u : 0u);
             }
-          } else {
-#pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              umma_bf16_ss_2cta(d_tmem, make_sw128_kmajor_desc(st + k * 32),
-                                make_sw128_kmajor_desc(st + kPanelBytes + k * 32), idesc, (ks | k) != 0 ? 1u : 0u);
+            umma_commit_2cta(smem_u32(&tail->empty[s]));
+            if (ks == n_ksteps - 1) umma_commit_2cta(smem_u32(&tail->tmem_full[as]));
           }
-          umma_commit_2cta(smem_u32(&tail->empty[s]));
-          if (ks == n_ksteps - 1) umma_commit_2cta(smem_u32(&tail->tmem_full[as]));
+          __syncwarp();
           if (++s == kStages) { s = 0; ph ^= 1u; }
         }
         as ^= 1;
