@@ -283,7 +283,7 @@ rbk_status refresh_corpus_tmap(rbk_index* ix) {
   if (st != RBK_OK) return st;
   st = encode_rows_tmap(&ix->tmap_c_pf, ix->rows, ix->n_rows, ix->dpad, kBlockN / 2, 256);
   if (st != RBK_OK) return st;
-  st = encode_rows_tmap(&ix->tmap_c_r32, ix->rows, ix->n_rows, ix->dpad, 32);
+  st = encode_rows_tmap(&ix->tmap_c_r32, ix->rows, ix->n_rows, ix->dpad, scan3_box_rows());
   if (st != RBK_OK) return st;
   ix->tmap_c_base = ix->rows;
   ix->tmap_c_rows = ix->n_rows;

@@ -50,6 +50,7 @@ cudaError_t launch_scan2(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, c
 // CTA-pair kernel with the query operand in TMEM (rbk_scan3.cu): dpad <= 768.  tmap_c: 32-row x 64-col boxes.
 cudaError_t launch_scan3(const CUtensorMap& tmap_c, const ScanParams& p, const uint16_t* q_bf16, cudaStream_t stream);
 bool scan3_fits(int dpad);
+int scan3_box_rows();   // corpus rows per CTA per TMA box of the TMEM-query kernel
 bool scan2_resident_fits(int dpad);
 int scan2_resident_k();   // corpus columns per stage of the resident kernel (64 or 32)
 

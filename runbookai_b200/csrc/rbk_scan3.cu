@@ -25,12 +25,19 @@ namespace rbk {
 
 namespace {
 
-constexpr int kSubN = 64;                       // corpus rows per accumulator (UMMA N)
+#ifndef RBK_TS_SUBN
+#define RBK_TS_SUBN 64
+#endif
+constexpr int kSubN = RBK_TS_SUBN;              // corpus rows per accumulator (UMMA N): 64 (2 buffers) or 128 (1)
+constexpr int kAccStages = kSubN == 64 ? 2 : 1;
 constexpr int kSubHalf = kSubN / 2;             // rows staged per CTA
-constexpr int kKbPerStage = 2;                  // 64-column k-blocks per ring stage
+#ifndef RBK_TS_KB_PER_STAGE
+#define RBK_TS_KB_PER_STAGE 4
+#endif
+constexpr int kKbPerStage = RBK_TS_KB_PER_STAGE; // 64-column k-blocks per ring stage (16 MMAs = 512 tensor cycles at 4)
 constexpr int kKbBytes = kSubHalf * kBlockK * 2;            // 4 KiB: 32 rows x 64 bf16
 constexpr int kStage3Bytes = kKbPerStage * kKbBytes;        // 8 KiB per CTA per stage
-constexpr int kStages3 = 24;                                // 192 KiB ring per CTA
+constexpr int kStages3 = 192 * 1024 / kStage3Bytes;         // 192 KiB ring per CTA
 constexpr int kTmemCols = 512;
 constexpr int kAccCol0 = 384;                               // accumulators live above the queries
 constexpr int kEpi = 128;
@@ -174,8 +181,7 @@ scan3_kernel(const __grid_constant__ CUtensorMap tmap_c, const ScanParams p, con
             __syncwarp();
             if (++s == kStages3) { s = 0; ph ^= 1u; }
           }
-          as ^= 1;
-          if (as == 0) aph ^= 1u;
+          if (++as == kAccStages) { as = 0; aph ^= 1u; }
         }
       }
     }
@@ -260,8 +266,7 @@ scan3_kernel(const __grid_constant__ CUtensorMap tmap_c, const ScanParams p, con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(smem_u32(&tail->tmem_empty[as]));
-        as ^= 1;
-        if (as == 0) aph ^= 1u;
+        if (++as == kAccStages) { as = 0; aph ^= 1u; }
       }
     }
     p.cand_cnt[(qb * p.R + r) * (2 * kBlockM) + qin] = fs.cnt;
@@ -276,6 +281,8 @@ scan3_kernel(const __grid_constant__ CUtensorMap tmap_c, const ScanParams p, con
 }
 
 }  // namespace
+
+int scan3_box_rows() { return kSubHalf; }
 
 // Queries fit TMEM next to two 64-column accumulators, and the ring stages hold whole k-block pairs.
 bool scan3_fits(int dpad) {

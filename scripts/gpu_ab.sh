@@ -1,6 +1,6 @@
 #!/bin/bash
 export PYTHONUNBUFFERED=1
-run() { echo "== $*"; env "$@" timeout 600 python scripts/gpu_check.py time1 time2 time3 2>&1 | python -c "
+run() { echo "== $*"; env "$@" timeout 600 python scripts/gpu_check.py time1 time2 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     try: j=json.loads(l)
@@ -8,4 +8,3 @@ for l in sys.stdin:
     print(j['stage'], 'b',j['b'],'n',j['n'], 'scan_ms', min(j['scan_ms'][1:]), 'tflops', round(j['tflops'],1), 'gbps', round(j['gbps']))
 "; }
 run RBK_KNN_TS=1
-run RBK_KNN_TS=0
