@@ -55,35 +55,43 @@ __device__ __forceinline__ void filter_init(FilterState& s, bool valid, float th
 }
 
 // Raise thr from the global histogram (source 3).  Per-thread, no warp collectives.
+// Bins are fetched 16 at a time (four independent 16-byte L2 loads in flight): a dependent chain
+// of single loads cost ~0.7 us per 4 bins and made this function 23 % of the epilogue's time.
 static __device__ __noinline__ void filter_refresh(FilterState& s, int kprime) {
   if (!s.valid) return;
   const int mb = __ldcg(s.maxbin_q);
   if (mb <= s.tb) return;
   const uint4* h4 = reinterpret_cast<const uint4*>(s.hist_q);
-  const int g_lo = (s.tb + 1) >> 2;
-  int g = mb >> 2;
+  const int g_lo = (s.tb + 1) >> 2;   // lowest group that may hold a bin > tb
   unsigned cum = 0;
-  uint4 cur = __ldcg(h4 + g);
-  while (true) {
-    uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
-    if (g > g_lo) nxt = __ldcg(h4 + g - 1);
-    const unsigned c[4] = {cur.x, cur.y, cur.z, cur.w};
+  for (int g_hi = mb >> 2; g_hi >= g_lo; g_hi -= 4) {
+    uint4 w[4];
 #pragma unroll
-    for (int j = 3; j >= 0; --j) {
-      const int b = g * 4 + j;
-      if (b <= mb && b > s.tb) {
-        cum += c[j];
-        if (cum >= static_cast<unsigned>(kprime)) {
-          s.tb = b;
-          s.thr = fmaxf(s.thr, bin_edge_raw(b, s.qn));
-          return;
+    for (int u = 0; u < 4; ++u) w[u] = (g_hi - u >= g_lo) ? __ldcg(h4 + g_hi - u) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int g = g_hi - u;
+      const unsigned c[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+      for (int j = 3; j >= 0; --j) {
+        const int b = g * 4 + j;
+        if (g >= g_lo && b <= mb && b > s.tb) {
+          cum += c[j];
+          if (cum >= static_cast<unsigned>(kprime)) {
+            s.tb = b;
+            s.thr = fmaxf(s.thr, bin_edge_raw(b, s.qn));
+            return;
+          }
         }
       }
     }
-    if (g <= g_lo) return;
-    --g;
-    cur = nxt;
   }
+}
+
+// When to refresh: every tile while the threshold is still moving fast, then ever more rarely
+// (a stale threshold only costs a few extra appends).
+__device__ __forceinline__ bool refresh_due(int it) {
+  return it != 0 && (it < 8 || (it < 64 && (it & 7) == 0) || (it & 31) == 0);
 }
 
 __device__ __forceinline__ void filter_append(FilterState& s, float t, uint32_t row) {
@@ -185,10 +193,11 @@ static __device__ __noinline__ void warp_compact(unsigned long long* list, int c
 }
 
 // Warp-collective: compact every lane's list that could overflow on the next chunk.
-__device__ __forceinline__ void filter_compact_if_needed(FilterState& s, int kprime, int lane) {
+// `room`: appends that may happen before the next call (32 per chunk processed in between).
+__device__ __forceinline__ void filter_compact_if_needed(FilterState& s, int kprime, int lane, int room = 32) {
   constexpr uint32_t kFullMask = 0xFFFFFFFFu;
   __syncwarp();
-  unsigned need = __ballot_sync(kFullMask, s.cnt > kListCap - 32);
+  unsigned need = __ballot_sync(kFullMask, s.cnt > kListCap - room);
   while (need) {
     const int src = __ffs(need) - 1;
     need &= need - 1;
@@ -245,16 +254,18 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
       nx1 = __ldg(p.inv_norm_c + (tile + 1) * kBlockN + kEpi + et);
     }
     named_bar_sync(1, kEpi);
-    if (it != 0 && (it < 8 || (it & 3) == 0)) filter_refresh(fs, p.kprime);   // overlaps this tile's MMAs
+    if (refresh_due(it)) filter_refresh(fs, p.kprime);   // overlaps this tile's MMAs
     mbar_wait(smem_u32(&tmem_full[as]), aph);
     tc_fence_after();
-#pragma unroll 1
-    for (int chunk = 0; chunk < kBlockN / 32; ++chunk) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                             static_cast<uint32_t>(as * kBlockN + chunk * 32),
-                         v);
-      tmem_wait_ld();
+    // Two chunks in flight: the TMEM load of the next 32 columns is issued before the current 32 are
+    // filtered, so its latency overlaps the arithmetic (one epilogue warp per SM sub-partition is
+    // latency-bound: ~1000 cycles per chunk measured with load -> wait -> compute in sequence).
+    const uint32_t tcol = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * kBlockN);
+    auto process = [&](uint32_t (&v)[32], int chunk) {
+      if (p.perf_probe == 1) {   // timing probe: keep the TMEM traffic, drop the arithmetic
+        if (v[0] == 0x7FC12345u) fs.cnt = 1;
+        return;
+      }
       filter_chunk(fs, v, invc + chunk * 32, static_cast<uint32_t>(row0 + chunk * 32));
       if (p.dbg_scores != nullptr && q_valid) {
 #pragma unroll
@@ -264,8 +275,20 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
             p.dbg_scores[static_cast<size_t>(q) * p.n_rows + row] = __uint_as_float(v[j]) * invc[chunk * 32 + j];
         }
       }
-      filter_compact_if_needed(fs, p.kprime, lane);
-      if (it == 0) filter_refresh(fs, p.kprime);   // start-up: converge within the first tile
+    };
+    uint32_t va[32], vb[32];
+    tmem_ld_32x32b_x32(tcol, va);
+#pragma unroll 1
+    for (int c2 = 0; c2 < kBlockN / 64; ++c2) {
+      tmem_wait_ld_dep(va);
+      tmem_ld_32x32b_x32(tcol + static_cast<uint32_t>((2 * c2 + 1) * 32), vb);
+      process(va, 2 * c2);
+      tmem_wait_ld_dep(vb);
+      if (c2 + 1 < kBlockN / 64) tmem_ld_32x32b_x32(tcol + static_cast<uint32_t>((2 * c2 + 2) * 32), va);
+      process(vb, 2 * c2 + 1);
+      filter_compact_if_needed(fs, p.kprime, lane, 64);
+      if (it == 0 && t1 - t0 > 2) filter_refresh(fs, p.kprime);   // start-up: converge within the first tile
+                                                                  // (pointless when the CTA owns a tile or two)
     }
     tc_fence_before();
     __syncwarp();

@@ -34,6 +34,7 @@ struct ScanParams {
   int num_kb;   // k-blocks per tile = ceil(dpad / kBlockK)
   int dpad;     // padded row length (elements)
   int prefetch_tiles;  // query-resident pair kernel: L2 prefetch distance in tiles (0 = off)
+  int perf_probe;      // 0 = normal.  TIMING EXPERIMENTS ONLY (results are wrong): 1 = epilogue drains TMEM but does not filter
   int QB;       // query blocks
   int R;        // corpus ranges (CTAs per query block)
   int n_tiles;  // ceil(n_rows / kBlockN)
@@ -52,6 +53,9 @@ cudaError_t launch_scan3(const CUtensorMap& tmap_c, const ScanParams& p, const u
 bool scan3_fits(int dpad);
 int scan3_box_rows();   // corpus rows per CTA per TMA box of the TMEM-query kernel
 bool scan2_resident_fits(int dpad);
+// Hybrid pair kernel: res_kb resident query panels, the rest + the corpus through n_slots 16-KB ring slots.
+cudaError_t launch_scan2h(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c_half, const ScanParams& p, int res_kb,
+                          int n_slots, cudaStream_t stream);
 int scan2_resident_k();   // corpus columns per stage of the resident kernel (64 or 32)
 
 // ---- ingest (rbk_ingest.cu) ----

@@ -231,6 +231,162 @@ scan2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
 
 constexpr size_t kMaxSmem = 232448;   // 227 KiB opt-in limit per CTA on sm_100
 
+// ---------------------------------------------------------------------------------------------
+// Hybrid variant: the first `res_kb` 64-column panels of the CTA's queries stay resident in smem,
+// the rest of the query slab and the whole corpus stream through a ring of 16 KB SLOTS (a k-block
+// whose query panel is resident takes one slot, a fully streamed k-block two).  Compared with the
+// fully streamed kernel this removes res_kb/num_kb of the query bytes from the L2->SM stream
+// (d=768, res_kb=6: 288 KB instead of 384 KB per CTA per 256x256 tile) while keeping a 128 KB
+// ring — the fully resident layout (32 KB ring) was latency-bound.
+constexpr int kSlotBytes = kPanelBytes;   // 16 KiB: 128 rows x 64 bf16, SWIZZLE_128B (queries or corpus half)
+constexpr int kMaxSlots = 10;
+
+struct SmemTailH {
+  float invc[2][kBlockN];
+  unsigned long long full[kMaxSlots];
+  unsigned long long empty[kMaxSlots];
+  unsigned long long tmem_full[2];
+  unsigned long long tmem_empty[2];
+  unsigned long long a_full;
+  uint32_t tmem_base;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kScanThreads, 1)
+scan2h_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
+              const ScanParams p, const int res_kb, const int n_slots) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  if (pad != 0) __trap();   // the layout is sized without slack: the dynamic smem base must be 1024-aligned
+  uint8_t* smem = smem_raw;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t ring_base = smem_base + static_cast<uint32_t>(res_kb) * kPanelBytes;
+  SmemTailH* tail = reinterpret_cast<SmemTailH*>(smem + (res_kb + n_slots) * kPanelBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int qb = pair % p.QB;
+  const int r = pair / p.QB;
+  const int t0 = static_cast<int>(static_cast<long long>(p.n_tiles) * r / p.R);
+  const int t1 = static_cast<int>(static_cast<long long>(p.n_tiles) * (r + 1) / p.R);
+  const int q_row0 = qb * 2 * kBlockM + static_cast<int>(rank) * kBlockM;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_c);
+    for (int s = 0; s < n_slots; ++s) {
+      mbar_init(smem_u32(&tail->full[s]), 1);
+      mbar_init(smem_u32(&tail->empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tail->tmem_full[a]), 1);
+      mbar_init(smem_u32(&tail->tmem_empty[a]), 8);
+    }
+    mbar_init(smem_u32(&tail->a_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(smem_u32(&tail->tmem_base), kTmemCols);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp, elected issue; both CTAs) =====================
+    if (res_kb > 0) {
+      const uint32_t a_full = smem_u32(&tail->a_full);
+      if (elect_one()) {
+        if (rank == 0) mbar_arrive_expect_tx(a_full, 2u * static_cast<uint32_t>(res_kb) * kPanelBytes);
+        for (int kb = 0; kb < res_kb; ++kb)
+          tma_load_2d_2cta(smem_base + kb * kPanelBytes, &tmap_q, a_full, kb * kBlockK, q_row0);
+      }
+      __syncwarp();
+    }
+    volatile int* prog = p.progress + r * p.QB;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = t0; tile < t1; ++tile) {
+      if (rank == 0 && lane == 0) lockstep_pace(prog, p.QB, qb, tile - t0);
+      __syncwarp();
+      const int c_row0 = tile * kBlockN + static_cast<int>(rank) * kHalfN;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int n_loads = kb < res_kb ? 1 : 2;   // [query panel,] corpus half-slab
+        for (int l = 2 - n_loads; l < 2; ++l) {
+          mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);
+          const uint32_t full = smem_u32(&tail->full[s]);
+          const uint32_t dst = ring_base + s * kSlotBytes;
+          if (elect_one()) {
+            if (rank == 0) mbar_arrive_expect_tx(full, 2 * kSlotBytes);   // both CTAs' bytes (see scan2_kernel)
+            if (l == 0) tma_load_2d_2cta(dst, &tmap_q, full, kb * kBlockK, q_row0);
+            else tma_load_2d_2cta(dst, &tmap_c, full, kb * kBlockK, c_row0);
+          }
+          __syncwarp();
+          if (++s == n_slots) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+    if (rank == 0 && lane == 0 && p.QB > 1) prog[qb] = 0x7FFFFFFF;
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA; whole warp, elected issue) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(2 * kBlockM, kBlockN);
+      int s = 0, as = 0;
+      uint32_t ph = 0, aph = 0;
+      if (res_kb > 0) {
+        mbar_wait(smem_u32(&tail->a_full), 0u);
+        tc_fence_after();
+      }
+      for (int tile = t0; tile < t1; ++tile) {
+        mbar_wait(smem_u32(&tail->tmem_empty[as]), aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * kBlockN);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          const bool streamed_a = kb >= res_kb;
+          uint32_t a_addr = smem_base + kb * kPanelBytes;
+          int sa = -1;
+          if (streamed_a) {
+            mbar_wait(smem_u32(&tail->full[s]), ph);
+            a_addr = ring_base + s * kSlotBytes;
+            sa = s;
+            if (++s == n_slots) { s = 0; ph ^= 1u; }
+          }
+          mbar_wait(smem_u32(&tail->full[s]), ph);
+          tc_fence_after();
+          const uint64_t adesc0 = make_sw128_kmajor_desc(a_addr);
+          const uint64_t bdesc0 = make_sw128_kmajor_desc(ring_base + s * kSlotBytes);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_bf16_ss_2cta(d_tmem, adesc0 + static_cast<uint64_t>(2 * k), bdesc0 + static_cast<uint64_t>(2 * k),
+                                idesc, (kb | k) != 0 ? 1u : 0u);
+            if (sa >= 0) umma_commit_2cta(smem_u32(&tail->empty[sa]));
+            umma_commit_2cta(smem_u32(&tail->empty[s]));
+            if (kb == p.num_kb - 1) umma_commit_2cta(smem_u32(&tail->tmem_full[as]));
+          }
+          __syncwarp();
+          if (++s == n_slots) { s = 0; ph ^= 1u; }
+        }
+        as ^= 1;
+        if (as == 0) aph ^= 1u;
+      }
+    }
+  } else {
+    run_epilogue<true>(p, tail->invc, tail->tmem_full, tail->tmem_empty, tmem_base, qb, r, rank, t0, t1, warp, lane);
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, kTmemCols);
+  }
+}
+
 }  // namespace
 
 // Can the query block stay resident for this padded dim?
@@ -259,6 +415,20 @@ cudaError_t launch_scan2(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, c
     if (e != cudaSuccess) return e;
     scan2_kernel<false><<<2 * p.QB * p.R, kScanThreads, smem, stream>>>(tmap_q, tmap_c, tmap_pf, p);
   }
+  return cudaGetLastError();
+}
+
+// Hybrid launch: res_kb resident query panels + n_slots ring slots (16 KB each) must fit 227 KB.
+cudaError_t launch_scan2h(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c_half, const ScanParams& p, int res_kb,
+                          int n_slots, cudaStream_t stream) {
+  if (res_kb > p.num_kb) res_kb = p.num_kb;
+  if (n_slots > kMaxSlots) n_slots = kMaxSlots;
+  if (n_slots < 4) n_slots = 4;
+  while (static_cast<size_t>(res_kb + n_slots) * kPanelBytes + sizeof(SmemTailH) > kMaxSmem && res_kb > 0) --res_kb;
+  const size_t smem = static_cast<size_t>(res_kb + n_slots) * kPanelBytes + sizeof(SmemTailH);
+  cudaError_t e = cudaFuncSetAttribute(scan2h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  scan2h_kernel<<<2 * p.QB * p.R, kScanThreads, smem, stream>>>(tmap_q, tmap_c_half, p, res_kb, n_slots);
   return cudaGetLastError();
 }
 

@@ -240,7 +240,7 @@ scan3_kernel(const __grid_constant__ CUtensorMap tmap_c, const ScanParams p, con
         nx1 = __ldg(p.inv_norm_c + (tile + 1) * kBlockN + kEpi + et);
       }
       named_bar_sync(1, kEpi);
-      if (it != 0 && (it < 8 || (it & 3) == 0)) filter_refresh(fs, p.kprime);
+      if (refresh_due(it)) filter_refresh(fs, p.kprime);
       for (int j = 0; j < kSubPerTile; ++j) {
         const int row0 = tile * kBlockN + j * kSubN;
         const float* invc = invc_tile + j * kSubN;
@@ -261,7 +261,7 @@ scan3_kernel(const __grid_constant__ CUtensorMap tmap_c, const ScanParams p, con
             }
           }
           filter_compact_if_needed(fs, p.kprime, lane);
-          if (it == 0) filter_refresh(fs, p.kprime);
+          if (it == 0 && t1 - t0 > 2) filter_refresh(fs, p.kprime);
         }
         tc_fence_before();
         __syncwarp();

@@ -12,7 +12,7 @@ if [ "$1" != "noncu" ]; then
 echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"scan_kernel|finalize_kernel|prep_queries|exact_|merge_shards" -c 200 --csv --log-file gpurun_out/launches_cfg3.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch_stdout.log 2>&1
 echo "== ncu full (scan kernel, cfg3)"
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:scan_kernel -s 3 -c 1 -f -o gpurun_out/scan_cfg3 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_stdout.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan_kernel -s 3 -c 1 -f -o gpurun_out/scan_cfg2 python bench.py --workload cfg2 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full2_stdout.log 2>&1
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:scan -s 3 -c 1 -f -o gpurun_out/scan_cfg3 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_stdout.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan -s 3 -c 1 -f -o gpurun_out/scan_cfg2 python bench.py --workload cfg2 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full2_stdout.log 2>&1
 fi
 ls -la gpurun_out
