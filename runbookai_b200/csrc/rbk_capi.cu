@@ -303,9 +303,8 @@ rbk_status ensure_query_scratch(rbk_index* ix, int B, int elem) {
   CK(ix->flags.ensure(B));
   CK(ix->cand.ensure(static_cast<size_t>(ix->sm_count) * kBlockM * kListCap));
   CK(ix->cand_cnt.ensure(static_cast<size_t>(ix->sm_count) * kBlockM));
-  CK(ix->hist.ensure(static_cast<size_t>(kMaxSubBatch) * kHistBins));
-  CK(ix->maxbin.ensure(kMaxSubBatch));
-  CK(ix->progress.ensure(static_cast<size_t>(ix->sm_count) + 8));
+  // hist [kMaxSubBatch][kHistBins] | maxbin [kMaxSubBatch] | progress [sm_count + 8]: one buffer, one memset
+  CK(ix->hist.ensure(static_cast<size_t>(kMaxSubBatch) * kHistBins + kMaxSubBatch + ix->sm_count + 8));
   return RBK_OK;
 }
 
@@ -355,12 +354,15 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
     sp.inv_norm_c = ix->inv_norm;
     sp.thr_init = ix->thr_init.p + q0;
     sp.inv_norm_q = ix->q_inv_norm.p + q0;
-    sp.hist = ix->hist.p;
-    sp.maxbin = ix->maxbin.p;
-    sp.progress = ix->progress.p;
-    CK(cudaMemsetAsync(ix->progress.p, 0, sizeof(int) * (static_cast<size_t>(ix->sm_count) + 8), ix->stream));
-    CK(cudaMemsetAsync(ix->hist.p, 0, sizeof(unsigned int) * static_cast<size_t>(Bs) * kHistBins, ix->stream));
-    CK(cudaMemsetAsync(ix->maxbin.p, 0, sizeof(int) * Bs, ix->stream));
+    {
+      // per-launch scratch, zeroed with one memset: hist rows of this sub-batch, then maxbin, then progress
+      unsigned int* base = ix->hist.p;
+      sp.hist = base;
+      sp.maxbin = reinterpret_cast<int*>(base + static_cast<size_t>(Bs) * kHistBins);
+      sp.progress = sp.maxbin + Bs;
+      CK(cudaMemsetAsync(base, 0, sizeof(unsigned int) * (static_cast<size_t>(Bs) * kHistBins + Bs + ix->sm_count + 8),
+                         ix->stream));
+    }
     sp.cand = ix->cand.p;
     sp.cand_cnt = ix->cand_cnt.p;
     sp.dbg_scores = dbg ? dbg + static_cast<size_t>(q0) * ix->n_rows : nullptr;

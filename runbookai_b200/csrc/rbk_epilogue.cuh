@@ -109,6 +109,7 @@ __device__ __forceinline__ void filter_append(FilterState& s, float t, uint32_t 
 __device__ __forceinline__ void filter_chunk(FilterState& s, const uint32_t (&v)[32], const float* invc32,
                                              uint32_t row_base) {
   const float4* ic4 = reinterpret_cast<const float4*>(invc32);
+  float g[8];   // maxima of the 8 groups of 4 columns (intermediates of the chunk maximum, kept for the slow path)
   float m = -INFINITY;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -117,13 +118,22 @@ __device__ __forceinline__ void filter_chunk(FilterState& s, const uint32_t (&v)
     const float a1 = __uint_as_float(v[4 * j + 1]) * w.y;
     const float a2 = __uint_as_float(v[4 * j + 2]) * w.z;
     const float a3 = __uint_as_float(v[4 * j + 3]) * w.w;
-    m = fmaxf(m, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));  // fmaxf drops NaN (dead / out-of-range rows)
+    g[j] = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));   // fmaxf drops NaN (dead / out-of-range rows)
+    m = fmaxf(m, g[j]);
   }
-  if (m > s.thr) {  // rare once the threshold has converged
+  if (m > s.thr) {
+    // Rare per LANE but not per WARP while thresholds are still converging (1024 (query,row) pairs per warp
+    // and chunk): walk only the groups of 4 that hold a survivor, so one lucky lane costs the warp a few
+    // dozen instructions instead of 32 predicated append blocks.
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float t = __uint_as_float(v[j]) * invc32[j];
-      if (t > s.thr) filter_append(s, t, row_base + j);
+    for (int j = 0; j < 8; ++j) {
+      if (g[j] > s.thr) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float t = __uint_as_float(v[4 * j + e]) * invc32[4 * j + e];
+          if (t > s.thr) filter_append(s, t, row_base + 4 * j + e);
+        }
+      }
     }
   }
 }

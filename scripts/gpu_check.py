@@ -100,6 +100,32 @@ def stage_time(n=1_000_000, d=768, b=256, k=32, iters=5, tag="time"):
     ix.close()
 
 
+def stage_sweep():
+    """scan time vs N at B=1024 (fixed per-launch cost of the scan kernel)."""
+    import numpy as np
+    import torch
+    from runbookai_b200 import Index, synth
+    d, b, k = 768, 1024, 32
+    q = synth.random_queries(b, d, 8).astype(np.float32)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    ix = Index(d, capacity_hint=4_000_000)
+    have = 0
+    for n in (65536, 262144, 524288, 1048576, 2097152, 4194304):
+        while have < n:
+            m = min(1 << 18, n - have)
+            t = torch.randn(m, d, device="cuda", generator=g, dtype=torch.float32).to(torch.bfloat16)
+            torch.cuda.synchronize()
+            ix.append_bf16_device(t.data_ptr(), m)
+            have += m
+        res = []
+        for it in range(12):
+            ix.search(q, k, None)
+            res.append(ix.stats()["last_scan_ms"])
+        emit("sweep", n=n, b=b, scan_ms_min=min(res[2:]), scan_ms_med=float(np.median(res[2:])),
+             total_ms=ix.stats()["last_total_ms"])
+    ix.close()
+
+
 STAGES = {
     "gemm": lambda: stage_gemm(),
     "gemm2": lambda: stage_gemm(n=3000, d=768, b=130, tag="gemm2"),
@@ -111,6 +137,7 @@ STAGES = {
     "time1": lambda: stage_time(),
     "time2": lambda: stage_time(n=2_000_000, b=1024, tag="time2"),
     "time3": lambda: stage_time(n=1_000_000, b=1, k=10, tag="time3"),
+    "sweep": lambda: stage_sweep(),
 }
 
 if __name__ == "__main__":
