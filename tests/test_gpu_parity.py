@@ -79,6 +79,9 @@ def test_scan_scores_within_error_bound(rb):
     (40_000, 1024, 256, 32, 0, None),   # config-4 width, k_fetch 64
     (20_000, 1536, 5, 56, 0, None),     # the reference's default d, max k_fetch
     (150_000, 768, 64, 16, 0, None),    # many tiles per CTA: running thresholds + compaction
+    (4000, 100, 200, 8, 12, 0.5),       # CTA-pair kernel with a padded, non-multiple-of-64 dim
+    (60_000, 384, 1100, 16, 0, None),   # > 1024 queries: two sub-batches (1024 + 76) in one call
+    (3000, 2048, 140, 5, 4, 0.5),       # wide rows (32 k-blocks), pair kernel
 ])
 def test_parity_shapes(rb, oracle_mod, n, d, b, k, planted, min_score):
     from runbookai_b200 import synth
