@@ -60,6 +60,13 @@ const char* rbk_last_error(void);
 /* dim: embedding length (any d >= 1).  device: CUDA ordinal.  capacity_hint: rows to
  * pre-allocate (0 = default); the index grows on demand. */
 rbk_status rbk_index_create(int32_t dim, int32_t device, int64_t capacity_hint, rbk_index** out);
+/* flags: RBK_INDEX_KEEP_F64 keeps, next to the bf16 rows the scan reads, the ORIGINAL values of every appended
+ * row as float64 (8*dim bytes per row; f32/bf16 inputs are widened exactly).  The exact re-rank then uses them:
+ * results are the reference's fp64 cosine bit for bit for ARBITRARY float64 embeddings (the SQLite BLOBs of
+ * vector-store.ts:71-88), not only for bf16-representable ones.  The scan's error bound grows by the largest
+ * angle between a row and its bf16 rounding, so more queries may take the exhaustive path on near-tied data. */
+#define RBK_INDEX_KEEP_F64 1u
+rbk_status rbk_index_create_ex(int32_t dim, int32_t device, int64_t capacity_hint, uint32_t flags, rbk_index** out);
 void rbk_index_destroy(rbk_index* idx); /* NULL is a no-op */
 
 /* Run all device work of this index on the given cudaStream_t (NULL = the index's own

@@ -56,7 +56,9 @@ napi_value New(napi_env env, napi_callback_info info) {
   if (argc > 1) napi_get_value_int32(env, argv[1], &device);
   if (argc > 2) napi_get_value_int64(env, argv[2], &hint);
   rbk_index* ix = nullptr;
-  if (rbk_index_create(dim, device, hint, &ix) != RBK_OK) return throw_rbk(env);   // no GPU -> throws, no fallback
+  // KEEP_F64: the reference stores float64 embeddings; keep them so results are exact for any input
+  if (rbk_index_create_ex(dim, device, hint, RBK_INDEX_KEEP_F64, &ix) != RBK_OK)
+    return throw_rbk(env);   // no GPU -> throws, no fallback
   NAPI_OK(napi_wrap(env, self, ix, finalize_index, nullptr, nullptr));
   return self;
 }

@@ -17,7 +17,7 @@ RBK_MAX_K_FETCH = 112
 
 # every symbol include/rbk_knn.h declares (tests check the .so exports all of them)
 SYMBOLS = [
-    "rbk_abi_version", "rbk_last_error", "rbk_index_create", "rbk_index_destroy", "rbk_index_set_stream",
+    "rbk_abi_version", "rbk_last_error", "rbk_index_create", "rbk_index_create_ex", "rbk_index_destroy", "rbk_index_set_stream",
     "rbk_index_set_slot_base", "rbk_index_append_f64", "rbk_index_append_f32", "rbk_index_append_bf16",
     "rbk_index_append_bf16_device", "rbk_index_overwrite_f64", "rbk_index_tombstone", "rbk_index_clear",
     "rbk_index_count", "rbk_index_size", "rbk_index_dim", "rbk_index_read_rows_bf16", "rbk_index_search_f64",
@@ -55,6 +55,7 @@ def _load() -> C.CDLL:
     lib.rbk_abi_version.restype = C.c_int
     lib.rbk_last_error.restype = C.c_char_p
     lib.rbk_index_create.argtypes = [i32, i32, i64, C.POINTER(vp)]
+    lib.rbk_index_create_ex.argtypes = [i32, i32, i64, C.c_uint32, C.POINTER(vp)]
     lib.rbk_index_destroy.argtypes = [vp]
     lib.rbk_index_destroy.restype = None
     lib.rbk_index_set_stream.argtypes = [vp, vp]
@@ -102,10 +103,11 @@ def ptr(a: np.ndarray | None):
 class Index:
     """Thin object wrapper over rbk_index* (one GPU shard)."""
 
-    def __init__(self, dim: int, device: int = 0, capacity_hint: int = 0):
+    def __init__(self, dim: int, device: int = 0, capacity_hint: int = 0, keep_f64: bool = False):
+        """keep_f64: RBK_INDEX_KEEP_F64 — exact for arbitrary float64 rows at 8*dim extra bytes per row."""
         self._h = None
         h = C.c_void_p()
-        check(lib.rbk_index_create(dim, device, capacity_hint, C.byref(h)))
+        check(lib.rbk_index_create_ex(dim, device, capacity_hint, 1 if keep_f64 else 0, C.byref(h)))
         self._h = h
         self.dim = dim
         self.device = device

@@ -127,8 +127,10 @@ struct rbk_index {
   uint16_t* rows = nullptr;
   float* inv_norm = nullptr;  // padded to a multiple of kBlockN (+ one tile), NaN-filled
   double* norm2 = nullptr;
+  double* rows_f64 = nullptr;   // optional exact-source sidecar [cap][dim] (RBK_INDEX_KEEP_F64)
+  bool keep_f64 = false;
   unsigned int* dead_bits = nullptr;
-  int* d_counter = nullptr;
+  int* d_counter = nullptr;   // [0] tombstone counter, [1] eps_c_max (float bits)
   cudaStream_t own_stream = nullptr, stream = nullptr;
   std::mutex mu;
   // ingest staging
@@ -193,8 +195,12 @@ rbk_status ensure_capacity(rbk_index* ix, int64_t need) {
   float* inv = nullptr;
   double* n2 = nullptr;
   unsigned int* dead = nullptr;
+  double* r64 = nullptr;
   const size_t dead_words = static_cast<size_t>((ncap + 31) / 32);
   cudaError_t e;
+  if (ix->keep_f64 &&
+      (e = cudaMalloc(reinterpret_cast<void**>(&r64), static_cast<size_t>(ncap) * ix->dim * 8)) != cudaSuccess)
+    return cuda_fail(e, "cudaMalloc(f64 sidecar)");
   if ((e = cudaMalloc(reinterpret_cast<void**>(&rows), static_cast<size_t>(ncap) * ix->dpad * 2)) != cudaSuccess ||
       (e = cudaMalloc(reinterpret_cast<void**>(&inv), static_cast<size_t>(inv_norm_len(ncap)) * 4)) != cudaSuccess ||
       (e = cudaMalloc(reinterpret_cast<void**>(&n2), static_cast<size_t>(ncap) * 8)) != cudaSuccess ||
@@ -203,6 +209,7 @@ rbk_status ensure_capacity(rbk_index* ix, int64_t need) {
     cudaFree(inv);
     cudaFree(n2);
     cudaFree(dead);
+    cudaFree(r64);
     return cuda_fail(e, "cudaMalloc(index storage)");
   }
   cudaStream_t st = ix->stream;
@@ -214,12 +221,17 @@ rbk_status ensure_capacity(rbk_index* ix, int64_t need) {
     CK(cudaMemcpyAsync(n2, ix->norm2, static_cast<size_t>(ix->n_rows) * 8, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(dead, ix->dead_bits, static_cast<size_t>((ix->n_rows + 31) / 32) * 4,
                        cudaMemcpyDeviceToDevice, st));
+    if (r64)
+      CK(cudaMemcpyAsync(r64, ix->rows_f64, static_cast<size_t>(ix->n_rows) * ix->dim * 8, cudaMemcpyDeviceToDevice,
+                         st));
   }
   CK(cudaStreamSynchronize(st));
   cudaFree(ix->rows);
   cudaFree(ix->inv_norm);
   cudaFree(ix->norm2);
   cudaFree(ix->dead_bits);
+  cudaFree(ix->rows_f64);
+  ix->rows_f64 = r64;
   ix->rows = rows;
   ix->inv_norm = inv;
   ix->norm2 = n2;
@@ -240,11 +252,12 @@ rbk_status append_rows(rbk_index* ix, const void* src, bool is_device, int elem,
   if (st != RBK_OK) return st;
   const int src_type = elem == 8 ? 0 : (elem == 4 ? 1 : 2);
   uint16_t* dst0 = ix->rows + static_cast<size_t>(ix->n_rows) * ix->dpad;
+  double* dst64 = ix->keep_f64 ? ix->rows_f64 + static_cast<size_t>(ix->n_rows) * ix->dim : nullptr;
   if (is_device) {
-    if (elem == 2 && ix->dpad == ix->dim) {
+    if (elem == 2 && ix->dpad == ix->dim && !ix->keep_f64) {
       CK(cudaMemcpyAsync(dst0, src, static_cast<size_t>(n) * ix->dim * 2, cudaMemcpyDeviceToDevice, ix->stream));
     } else {
-      CK(launch_convert_rows(src, src_type, n, ix->dim, ix->dpad, dst0, ix->stream));
+      CK(launch_convert_rows(src, src_type, n, ix->dim, ix->dpad, dst0, dst64, ix->stream));
       ix->stats.kernel_launches++;
     }
   } else {
@@ -256,13 +269,14 @@ rbk_status append_rows(rbk_index* ix, const void* src, bool is_device, int elem,
       const unsigned char* hp = static_cast<const unsigned char*>(src) + static_cast<size_t>(r0) * row_bytes;
       CK(cudaMemcpyAsync(ix->stage.p, hp, static_cast<size_t>(nr) * row_bytes, cudaMemcpyHostToDevice, ix->stream));
       CK(launch_convert_rows(ix->stage.p, src_type, nr, ix->dim, ix->dpad, dst0 + static_cast<size_t>(r0) * ix->dpad,
-                             ix->stream));
+                             dst64 ? dst64 + static_cast<size_t>(r0) * ix->dim : nullptr, ix->stream));
       ix->stats.kernel_launches++;
       // the staging buffer is reused by the next chunk; pageable H2D copies are already
       // synchronous with respect to the host buffer, the kernel is ordered by the stream
     }
   }
-  CK(launch_row_norms(dst0, n, ix->dim, ix->dpad, ix->inv_norm + ix->n_rows, ix->norm2 + ix->n_rows, ix->stream));
+  CK(launch_row_norms(dst0, dst64, n, ix->dim, ix->dpad, ix->inv_norm + ix->n_rows, ix->norm2 + ix->n_rows,
+                      ix->d_counter + 1, ix->stream));
   ix->stats.kernel_launches++;
   CK(cudaStreamSynchronize(ix->stream));
   ix->n_rows += n;
@@ -324,7 +338,9 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
                     long long* d_slots, double* d_scores, int* d_counts, float* dbg, size_t* ev_cursor) {
   const int kprime = pick_kprime(ix, k_fetch);
   ix->stats.last_kprime = kprime;
-  CK(launch_prep_queries(d_q, src_type, B, ix->dim, ix->dpad, min_score, query_buffers(ix, 0), ix->stream));
+  CK(launch_prep_queries(d_q, src_type, B, ix->dim, ix->dpad, min_score,
+                         ix->keep_f64 ? reinterpret_cast<const float*>(ix->d_counter + 1) : nullptr,
+                         query_buffers(ix, 0), ix->stream));
   ix->stats.kernel_launches++;
   if (ix->n_rows == 0) {
     // nothing to scan: finalize would read unwritten lists; emit empty results directly
@@ -405,6 +421,7 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
       fp.block_m = block_m;
       fp.min_score = min_score;
       fp.rows = ix->rows;
+      fp.rows_f64 = ix->rows_f64;
       fp.row_norm2 = ix->norm2;
       fp.n_rows = ix->n_rows;
       fp.slot_base = ix->slot_base;
@@ -437,8 +454,9 @@ rbk_status run_fallback(rbk_index* ix, const std::vector<int>& fails, int k_fetc
   ep.k_fetch = k_fetch;
   ep.min_score = min_score;
   ep.rows = ix->rows;
+  ep.rows_f64 = ix->rows_f64;
   ep.row_norm2 = ix->norm2;
-  ep.inv_norm_c = ix->inv_norm;
+  ep.dead_bits = ix->dead_bits;
   ep.n_rows = ix->n_rows;
   ep.slot_base = ix->slot_base;
   ep.q_f64 = ix->q_f64.p;
@@ -549,7 +567,12 @@ int rbk_abi_version(void) { return RBK_ABI_VERSION; }
 const char* rbk_last_error(void) { return g_err.c_str(); }
 
 rbk_status rbk_index_create(int32_t dim, int32_t device, int64_t capacity_hint, rbk_index** out) {
+  return rbk_index_create_ex(dim, device, capacity_hint, 0, out);
+}
+
+rbk_status rbk_index_create_ex(int32_t dim, int32_t device, int64_t capacity_hint, uint32_t flags, rbk_index** out) {
   if (!out) return fail(RBK_EINVAL, "out is null");
+  if (flags & ~static_cast<uint32_t>(RBK_INDEX_KEEP_F64)) return fail(RBK_EINVAL, "unknown flag");
   *out = nullptr;
   if (dim < 1 || dim > (1 << 20)) return fail(RBK_EINVAL, "dim out of range");
   int ndev = 0;
@@ -568,6 +591,7 @@ rbk_status rbk_index_create(int32_t dim, int32_t device, int64_t capacity_hint, 
   ix->dim = dim;
   ix->dpad = static_cast<int>(round_up(dim, 8));
   ix->device = device;
+  ix->keep_f64 = (flags & RBK_INDEX_KEEP_F64) != 0;
   ix->sm_count = prop.multiProcessorCount;
   memset(&ix->stats, 0, sizeof ix->stats);
   ix->stats.sm_count = ix->sm_count;
@@ -585,7 +609,8 @@ rbk_status rbk_index_create(int32_t dim, int32_t device, int64_t capacity_hint, 
     return cuda_fail(e, "cudaStreamCreate");
   }
   ix->stream = ix->own_stream;
-  e = cudaMalloc(reinterpret_cast<void**>(&ix->d_counter), sizeof(int));
+  e = cudaMalloc(reinterpret_cast<void**>(&ix->d_counter), 2 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(ix->d_counter, 0, 2 * sizeof(int));
   if (e != cudaSuccess) {
     rbk_index_destroy(ix);
     return cuda_fail(e, "cudaMalloc");
@@ -608,6 +633,7 @@ void rbk_index_destroy(rbk_index* ix) {
     cudaFree(ix->inv_norm);
     cudaFree(ix->norm2);
     cudaFree(ix->dead_bits);
+    cudaFree(ix->rows_f64);
     cudaFree(ix->d_counter);
     ix->stage.release();
     ix->d_slots.release();
@@ -687,8 +713,10 @@ rbk_status rbk_index_overwrite_f64(rbk_index* ix, int64_t slot, const double* ro
   CK(ix->stage.ensure(static_cast<size_t>(ix->dim) * 8));
   CK(cudaMemcpyAsync(ix->stage.p, row, static_cast<size_t>(ix->dim) * 8, cudaMemcpyHostToDevice, ix->stream));
   uint16_t* dst = ix->rows + static_cast<size_t>(slot) * ix->dpad;
-  CK(launch_convert_rows(ix->stage.p, 0, 1, ix->dim, ix->dpad, dst, ix->stream));
-  CK(launch_row_norms(dst, 1, ix->dim, ix->dpad, ix->inv_norm + slot, ix->norm2 + slot, ix->stream));
+  double* dst64 = ix->keep_f64 ? ix->rows_f64 + static_cast<size_t>(slot) * ix->dim : nullptr;
+  CK(launch_convert_rows(ix->stage.p, 0, 1, ix->dim, ix->dpad, dst, dst64, ix->stream));
+  CK(launch_row_norms(dst, dst64, 1, ix->dim, ix->dpad, ix->inv_norm + slot, ix->norm2 + slot, ix->d_counter + 1,
+                      ix->stream));
   ix->stats.kernel_launches += 2;
   CK(cudaStreamSynchronize(ix->stream));
   return RBK_OK;
@@ -720,6 +748,7 @@ rbk_status rbk_index_clear(rbk_index* ix) {
   DeviceGuard dg(ix->device);
   CK(cudaMemsetAsync(ix->inv_norm, 0xFF, static_cast<size_t>(inv_norm_len(ix->cap)) * 4, ix->stream));
   CK(cudaMemsetAsync(ix->dead_bits, 0, static_cast<size_t>((ix->cap + 31) / 32) * 4, ix->stream));
+  CK(cudaMemsetAsync(ix->d_counter, 0, 2 * sizeof(int), ix->stream));   // also resets the corpus-side error bound
   CK(cudaStreamSynchronize(ix->stream));
   ix->n_rows = 0;
   ix->n_live = 0;

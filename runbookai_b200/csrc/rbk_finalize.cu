@@ -40,6 +40,12 @@ __device__ __forceinline__ double exact_dot(const double* __restrict__ q, const 
   for (; i < d; ++i) dot = __dadd_rn(dot, __dmul_rn(__ldg(q + i), bf16_to_f64(row[i])));
   return dot;
 }
+// same, f64 sidecar row
+__device__ __forceinline__ double exact_dot_f64(const double* __restrict__ q, const double* __restrict__ row, int d) {
+  double dot = 0.0;
+  for (int i = 0; i < d; ++i) dot = __dadd_rn(dot, __dmul_rn(__ldg(q + i), __ldg(row + i)));
+  return dot;
+}
 // embedder.ts:183  dotProduct / (Math.sqrt(normA) * Math.sqrt(normB))
 __device__ __forceinline__ double exact_cosine(double dot, double na, double nb) {
   return __ddiv_rn(dot, __dmul_rn(__dsqrt_rn(na), __dsqrt_rn(nb)));
@@ -48,7 +54,8 @@ __device__ __forceinline__ double exact_cosine(double dot, double na, double nb)
 // --------------------------------------------------------------------------- prep
 template <typename SrcT>
 __global__ void __launch_bounds__(128) prep_queries_kernel(const SrcT* __restrict__ src, int d, int dpad,
-                                                           double min_score, double acc_eps, QueryBuffers qb) {
+                                                           double min_score, double acc_eps,
+                                                           const float* __restrict__ eps_c, QueryBuffers qb) {
   const int q = blockIdx.x;
   const int tid = threadIdx.x;
   const SrcT* s = src + static_cast<size_t>(q) * d;
@@ -99,7 +106,8 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const SrcT* __restric
       const double ratio = sqrt(nd2 / na) * (1.0 + 1e-9);
       ang = ratio < 1.0 ? asin(ratio) * (1.0 + 1e-9) : 3.2;
     }
-    const double eps = acc_eps + ang;
+    // + corpus-side quantisation angle when the exact source is an f64 sidecar (0 for bf16-exact corpora)
+    const double eps = acc_eps + ang + (eps_c != nullptr ? static_cast<double>(*eps_c) * (1.0 + 1e-6) : 0.0);
     qb.q_norm2[q] = na;
     qb.q_eps[q] = eps;
     const float invf = ok ? static_cast<float>(inv) : __uint_as_float(0x7FC00000u);
@@ -293,39 +301,62 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p)
   const double* qv = p.q.q_f64 + static_cast<size_t>(ql) * p.d;
   __shared__ double s_q[kQChunk];
   unsigned char* s_rows = reinterpret_cast<unsigned char*>(s_keys);
-  int chunk = nsel > 0 ? ((p.key_cap * 8 / nsel - 16) / 2) & ~7 : kQChunk;
-  chunk = chunk < kQChunk ? chunk : kQChunk;
-  const int chunk16 = chunk >> 3;                                   // 16-byte units per row chunk
-  const int row_stride = (chunk16 | 1) << 4;                        // odd number of 16-B units: conflict-free walks
   int my_row = 0;
   double dot = 0.0;
   if (tid < nsel) my_row = static_cast<int>(key_row(s_sel[tid]));
-  for (int c0 = 0; c0 < p.d; c0 += chunk) {
-    const int len = p.d - c0 < chunk ? p.d - c0 : chunk;            // elements of this chunk
-    const int len16 = (len + 7) >> 3;                               // rows are zero padded to dpad (multiple of 8)
-    __syncthreads();                                                // previous chunk fully consumed
-    for (int i = tid; i < nsel * len16; i += kFinThreads) {
-      const int rr = i / len16, u = i - rr * len16;
-      const int row = static_cast<int>(key_row(s_sel[rr]));
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.rows + static_cast<size_t>(row) * p.dpad + c0) + u);
-      *reinterpret_cast<uint4*>(s_rows + rr * row_stride + u * 16) = v;
-    }
-    for (int i = tid; i < len; i += kFinThreads) s_q[i] = __ldg(qv + c0 + i);
-    __syncthreads();
-    if (tid < nsel) {
-      const unsigned char* mine = s_rows + tid * row_stride;
-      int i = 0;
-      for (; i + 8 <= len; i += 8) {
-        const uint4 v = *reinterpret_cast<const uint4*>(mine + i * 2);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          dot = __dadd_rn(dot, __dmul_rn(s_q[i + 2 * j], bf16_to_f64(w[j] & 0xFFFFu)));
-          dot = __dadd_rn(dot, __dmul_rn(s_q[i + 2 * j + 1], bf16_to_f64(w[j] >> 16)));
-        }
+  if (p.rows_f64 == nullptr) {
+    int chunk = nsel > 0 ? ((p.key_cap * 8 / nsel - 16) / 2) & ~7 : kQChunk;
+    chunk = chunk < kQChunk ? chunk : kQChunk;
+    const int chunk16 = chunk >> 3;                                   // 16-byte units per row chunk
+    const int row_stride = (chunk16 | 1) << 4;                        // odd number of 16-B units: conflict-free walks
+    for (int c0 = 0; c0 < p.d; c0 += chunk) {
+      const int len = p.d - c0 < chunk ? p.d - c0 : chunk;            // elements of this chunk
+      const int len16 = (len + 7) >> 3;                               // rows are zero padded to dpad (multiple of 8)
+      __syncthreads();                                                // previous chunk fully consumed
+      for (int i = tid; i < nsel * len16; i += kFinThreads) {
+        const int rr = i / len16, u = i - rr * len16;
+        const int row = static_cast<int>(key_row(s_sel[rr]));
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.rows + static_cast<size_t>(row) * p.dpad + c0) + u);
+        *reinterpret_cast<uint4*>(s_rows + rr * row_stride + u * 16) = v;
       }
-      for (; i < len; ++i)
-        dot = __dadd_rn(dot, __dmul_rn(s_q[i], bf16_to_f64(reinterpret_cast<const uint16_t*>(mine)[i])));
+      for (int i = tid; i < len; i += kFinThreads) s_q[i] = __ldg(qv + c0 + i);
+      __syncthreads();
+      if (tid < nsel) {
+        const unsigned char* mine = s_rows + tid * row_stride;
+        int i = 0;
+        for (; i + 8 <= len; i += 8) {
+          const uint4 v = *reinterpret_cast<const uint4*>(mine + i * 2);
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            dot = __dadd_rn(dot, __dmul_rn(s_q[i + 2 * j], bf16_to_f64(w[j] & 0xFFFFu)));
+            dot = __dadd_rn(dot, __dmul_rn(s_q[i + 2 * j + 1], bf16_to_f64(w[j] >> 16)));
+          }
+        }
+        for (; i < len; ++i)
+          dot = __dadd_rn(dot, __dmul_rn(s_q[i], bf16_to_f64(reinterpret_cast<const uint16_t*>(mine)[i])));
+      }
+    }
+  } else {
+    // exact source = the f64 sidecar: same staging, 8-byte elements (odd stride in doubles: conflict-free)
+    double* s_rows64 = reinterpret_cast<double*>(s_keys);
+    int chunk = nsel > 0 ? (p.key_cap / nsel - 1) : kQChunk;          // doubles per row chunk
+    chunk = chunk < kQChunk ? chunk : kQChunk;
+    const int row_stride = chunk | 1;
+    for (int c0 = 0; c0 < p.d; c0 += chunk) {
+      const int len = p.d - c0 < chunk ? p.d - c0 : chunk;
+      __syncthreads();
+      for (int i = tid; i < nsel * len; i += kFinThreads) {
+        const int rr = i / len, u = i - rr * len;
+        const int row = static_cast<int>(key_row(s_sel[rr]));
+        s_rows64[rr * row_stride + u] = __ldg(p.rows_f64 + static_cast<size_t>(row) * p.d + c0 + u);
+      }
+      for (int i = tid; i < len; i += kFinThreads) s_q[i] = __ldg(qv + c0 + i);
+      __syncthreads();
+      if (tid < nsel) {
+        const double* mine = s_rows64 + tid * row_stride;
+        for (int i = 0; i < len; ++i) dot = __dadd_rn(dot, __dmul_rn(s_q[i], mine[i]));
+      }
     }
   }
   if (tid < nsel) {
@@ -460,9 +491,11 @@ __global__ void __launch_bounds__(kExThreads) exact_scan_kernel(ExactParams p) {
     if (t.n > kExBuf - kExThreads) exact_compact(t, p.k_fetch);  // uniform: t.n read after a barrier
     const int64_t row = base + tid;
     if (row < r1) {
-      const float ic = p.inv_norm_c[row];
-      if (ic == ic) {  // live, non-zero row
-        const double dot = exact_dot(qv, p.rows + static_cast<size_t>(row) * p.dpad, p.d);
+      const bool dead = (p.dead_bits[row >> 5] >> (row & 31)) & 1u;
+      if (!dead) {   // zero-norm rows give NaN and fail the compare below, like in the reference (S3)
+        const double dot = p.rows_f64 != nullptr
+                               ? exact_dot_f64(qv, p.rows_f64 + static_cast<size_t>(row) * p.d, p.d)
+                               : exact_dot(qv, p.rows + static_cast<size_t>(row) * p.dpad, p.d);
         const double sc = exact_cosine(dot, na, p.row_norm2[row]);
         if (sc >= p.min_score) exact_push(t, sc, static_cast<int>(row));
       }
@@ -570,13 +603,13 @@ __global__ void __launch_bounds__(128) merge_shards_kernel(int G, int B, int k, 
 }  // namespace
 
 cudaError_t launch_prep_queries(const void* src, int src_type, int B, int d, int dpad, double min_score,
-                                const QueryBuffers& qb, cudaStream_t stream) {
+                                const float* eps_c, const QueryBuffers& qb, cudaStream_t stream) {
   if (B <= 0) return cudaSuccess;
   const double acc_eps = accumulation_eps(d);
   if (src_type == 0)
-    prep_queries_kernel<double><<<B, 128, 0, stream>>>(static_cast<const double*>(src), d, dpad, min_score, acc_eps, qb);
+    prep_queries_kernel<double><<<B, 128, 0, stream>>>(static_cast<const double*>(src), d, dpad, min_score, acc_eps, eps_c, qb);
   else
-    prep_queries_kernel<float><<<B, 128, 0, stream>>>(static_cast<const float*>(src), d, dpad, min_score, acc_eps, qb);
+    prep_queries_kernel<float><<<B, 128, 0, stream>>>(static_cast<const float*>(src), d, dpad, min_score, acc_eps, eps_c, qb);
   return cudaGetLastError();
 }
 

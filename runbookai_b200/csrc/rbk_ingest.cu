@@ -26,7 +26,8 @@ __device__ __forceinline__ uint16_t f32_to_bf16_bits(float x) {
 // One thread produces 8 consecutive output elements (one 16-byte store).
 template <typename SrcT>
 __global__ void __launch_bounds__(256) convert_rows_kernel(const SrcT* __restrict__ src, int64_t n_rows, int d,
-                                                           int dpad, uint16_t* __restrict__ dst, bool aligned) {
+                                                           int dpad, uint16_t* __restrict__ dst,
+                                                           double* __restrict__ dst_f64, bool aligned) {
   const int groups = dpad >> 3;
   const int64_t total = n_rows * groups;
   for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < total;
@@ -70,6 +71,18 @@ __global__ void __launch_bounds__(256) convert_rows_kernel(const SrcT* __restric
         o[j] = b;
       }
     }
+    if (dst_f64 != nullptr) {   // exact-source sidecar: the original values, widened to f64 (pitch d)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (c0 + j < d) {
+          double x;
+          if constexpr (sizeof(SrcT) == 8) x = static_cast<double>(s[j]);
+          else if constexpr (sizeof(SrcT) == 4) x = static_cast<double>(static_cast<float>(s[j]));
+          else x = static_cast<double>(__uint_as_float(static_cast<uint32_t>(s[j]) << 16));
+          dst_f64[row * d + c0 + j] = x;
+        }
+      }
+    }
     uint4 out;
     out.x = o[0] | (static_cast<uint32_t>(o[1]) << 16);
     out.y = o[2] | (static_cast<uint32_t>(o[3]) << 16);
@@ -84,8 +97,14 @@ __device__ __forceinline__ double bf16_bits_to_f64(uint32_t h) {
 }
 
 // One thread per row: the accumulation order is part of the parity contract.
-__global__ void __launch_bounds__(128) row_norms_kernel(const uint16_t* __restrict__ rows, int64_t n_rows, int dpad,
-                                                        float* __restrict__ inv_norm, double* __restrict__ norm2) {
+// rows_f64 == nullptr: the bf16 row IS the corpus row, norm2 is its exact sequential sum of squares.
+// rows_f64 != nullptr: the f64 sidecar is the corpus row (norm2 from it); the bf16 row only feeds the
+//   approximate scan, and the angle between the two (an upper bound on how far the approximate cosine of
+//   this row can be from its true cosine, on top of the other error terms) is folded into *eps_c_max.
+__global__ void __launch_bounds__(128) row_norms_kernel(const uint16_t* __restrict__ rows,
+                                                        const double* __restrict__ rows_f64, int64_t n_rows, int d,
+                                                        int dpad, float* __restrict__ inv_norm,
+                                                        double* __restrict__ norm2, int* __restrict__ eps_c_max) {
   const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (row >= n_rows) return;
   const uint4* p = reinterpret_cast<const uint4*>(rows + row * dpad);
@@ -101,9 +120,29 @@ __global__ void __launch_bounds__(128) row_norms_kernel(const uint16_t* __restri
       acc = __dadd_rn(acc, __dmul_rn(hi, hi));
     }
   }
-  norm2[row] = acc;
   const bool ok = acc > 0.0 && acc < INFINITY;
   inv_norm[row] = ok ? static_cast<float>(1.0 / sqrt(acc)) : __uint_as_float(0x7FC00000u);
+  if (rows_f64 == nullptr) {
+    norm2[row] = acc;
+    return;
+  }
+  const double* x = rows_f64 + row * d;
+  const uint16_t* xb = rows + row * dpad;
+  double n2 = 0.0, diff2 = 0.0;
+  for (int i = 0; i < d; ++i) {
+    const double v = x[i];
+    n2 = __dadd_rn(n2, __dmul_rn(v, v));   // the reference's normB for the f64 row
+    const double e = v - bf16_bits_to_f64(xb[i]);
+    diff2 += e * e;
+  }
+  norm2[row] = n2;
+  float eps = 0.f;
+  if (diff2 > 0.0) {
+    const double ratio = (n2 > 0.0 && n2 < INFINITY) ? sqrt(diff2 / n2) * (1.0 + 1e-9) : 2.0;
+    eps = static_cast<float>((ratio < 1.0 ? asin(ratio) : 3.2) * (1.0 + 1e-6)) ;
+    eps = nextafterf(eps, INFINITY);
+  }
+  if (eps > 0.f) atomicMax(eps_c_max, __float_as_int(eps));   // non-negative floats order like ints
 }
 
 __global__ void tombstone_kernel(const int64_t* __restrict__ slots, int64_t n, int64_t n_rows,
@@ -131,7 +170,7 @@ int grid_for(int64_t items, int threads, int max_blocks) {
 }  // namespace
 
 cudaError_t launch_convert_rows(const void* src, int src_type, int64_t n_rows, int d, int dpad, uint16_t* dst_rows,
-                                cudaStream_t stream) {
+                                double* dst_f64, cudaStream_t stream) {
   if (n_rows <= 0) return cudaSuccess;
   const int64_t total = n_rows * (dpad >> 3);
   const int grid = grid_for(total, 256, 148 * 16);
@@ -139,22 +178,22 @@ cudaError_t launch_convert_rows(const void* src, int src_type, int64_t n_rows, i
   const bool aligned = (d & 7) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
   if (src_type == 0)
     convert_rows_kernel<double>
-        <<<grid, 256, 0, stream>>>(static_cast<const double*>(src), n_rows, d, dpad, dst_rows, aligned);
+        <<<grid, 256, 0, stream>>>(static_cast<const double*>(src), n_rows, d, dpad, dst_rows, dst_f64, aligned);
   else if (src_type == 1)
     convert_rows_kernel<float>
-        <<<grid, 256, 0, stream>>>(static_cast<const float*>(src), n_rows, d, dpad, dst_rows, aligned);
+        <<<grid, 256, 0, stream>>>(static_cast<const float*>(src), n_rows, d, dpad, dst_rows, dst_f64, aligned);
   else
     convert_rows_kernel<uint16_t>
-        <<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(src), n_rows, d, dpad, dst_rows, aligned);
+        <<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(src), n_rows, d, dpad, dst_rows, dst_f64, aligned);
   return cudaGetLastError();
 }
 
-cudaError_t launch_row_norms(const uint16_t* rows, int64_t n_rows, int d, int dpad, float* inv_norm, double* norm2,
-                             cudaStream_t stream) {
-  (void)d;
+cudaError_t launch_row_norms(const uint16_t* rows, const double* rows_f64, int64_t n_rows, int d, int dpad,
+                             float* inv_norm, double* norm2, int* eps_c_max, cudaStream_t stream) {
   if (n_rows <= 0) return cudaSuccess;
   const int64_t blocks = (n_rows + 127) / 128;
-  row_norms_kernel<<<static_cast<unsigned>(blocks), 128, 0, stream>>>(rows, n_rows, dpad, inv_norm, norm2);
+  row_norms_kernel<<<static_cast<unsigned>(blocks), 128, 0, stream>>>(rows, rows_f64, n_rows, d, dpad, inv_norm, norm2,
+                                                                      eps_c_max);
   return cudaGetLastError();
 }
 

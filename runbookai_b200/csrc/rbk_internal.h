@@ -60,10 +60,13 @@ int scan2_resident_k();   // corpus columns per stage of the resident kernel (64
 
 // ---- ingest (rbk_ingest.cu) ----
 // src element type: 0 = f64, 1 = f32, 2 = bf16 bits.  src is device memory, row pitch = d.
+// dst_f64 (nullable): exact-source sidecar rows, pitch d.
 cudaError_t launch_convert_rows(const void* src, int src_type, int64_t n_rows, int d, int dpad,
-                                uint16_t* dst_rows, cudaStream_t stream);
-cudaError_t launch_row_norms(const uint16_t* rows, int64_t n_rows, int d, int dpad, float* inv_norm,
-                             double* norm2, cudaStream_t stream);
+                                uint16_t* dst_rows, double* dst_f64, cudaStream_t stream);
+// rows_f64 (nullable): when given, norm2 comes from it and the bf16-vs-f64 angle bound is max-ed into *eps_c_max
+// (float bits in an int).
+cudaError_t launch_row_norms(const uint16_t* rows, const double* rows_f64, int64_t n_rows, int d, int dpad,
+                             float* inv_norm, double* norm2, int* eps_c_max, cudaStream_t stream);
 cudaError_t launch_tombstone(const int64_t* dev_slots, int64_t n, int64_t n_rows, float* inv_norm,
                              unsigned int* dead_bits, int* n_killed, cudaStream_t stream);
 
@@ -77,8 +80,9 @@ struct QueryBuffers {
   float* thr_init;     // [B]
 };
 // src_type: 0 = f64, 1 = f32 (device pointers, row pitch d)
+// eps_c (nullable): device float, bound on the corpus-side quantisation angle (f64 sidecar indexes).
 cudaError_t launch_prep_queries(const void* src, int src_type, int B, int d, int dpad, double min_score,
-                                const QueryBuffers& qb, cudaStream_t stream);
+                                const float* eps_c, const QueryBuffers& qb, cudaStream_t stream);
 
 struct FinalizeParams {
   const unsigned long long* cand;
@@ -89,6 +93,7 @@ struct FinalizeParams {
   int q0;  // global index of the first query of this launch (sub-batch offset)
   double min_score;
   const uint16_t* rows;
+  const double* rows_f64;   // nullable: exact-source sidecar (pitch d); the re-rank reads it instead of `rows`
   const double* row_norm2;
   int64_t n_rows;
   int64_t slot_base;
@@ -106,8 +111,9 @@ struct ExactParams {
   int d, dpad, k_fetch;
   double min_score;
   const uint16_t* rows;
+  const double* rows_f64;   // nullable: exact-source sidecar
   const double* row_norm2;
-  const float* inv_norm_c;  // NaN marks dead rows
+  const unsigned int* dead_bits;  // tombstones
   int64_t n_rows;
   int64_t slot_base;
   const double* q_f64;

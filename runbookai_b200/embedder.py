@@ -116,7 +116,7 @@ def find_most_similar(query_embedding, embeddings, top_k: int = 10, device: int 
     if not items:
         return []
     out = []
-    with Index(q.shape[0], device=device, capacity_hint=len(items)) as ix:
+    with Index(q.shape[0], device=device, capacity_hint=len(items), keep_f64=True) as ix:
         ix.append_f64(np.asarray([v for _, v in items], dtype=np.float64))
         for k0 in range(0, top_k, 112):  # the ABI serves at most 112 per call; page by exclusion
             k = min(112, top_k - k0)

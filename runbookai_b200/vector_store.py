@@ -77,7 +77,8 @@ class VectorStore:
     def __init__(self, db_path: str, device: int | None = None, index_factory=None):
         # index_factory(dim, device) -> object with the _native.Index surface; tests inject a
         # CPU stand-in to exercise the host logic where there is no GPU
-        self._index_factory = index_factory or (lambda dim, dev: Index(dim, device=dev))
+        # keep_f64: the reference stores float64 embeddings; keep them so the re-rank is exact for any input
+        self._index_factory = index_factory or (lambda dim, dev: Index(dim, device=dev, keep_f64=True))
         self.db = sqlite3.connect(db_path)
         self.db.row_factory = sqlite3.Row
         self.device = int(os.environ.get("RUNBOOK_KNN_DEVICE", "0")) if device is None else device

@@ -240,6 +240,52 @@ def test_non_bf16_queries_stay_exact(rb, oracle_mod):
         check_against_oracle(oracle_mod, ix, corpus, q, 10, None)
 
 
+def check_f64_index(oracle_mod, ix, corpus_f64, queries, k_fetch, min_score, live=None):
+    slots, scores, counts, _ = ix.search(queries, k_fetch, min_score)
+    for b in range(queries.shape[0]):
+        es, ev = oracle_mod.search(corpus_f64, queries[b], k_fetch, min_score, live=live)
+        assert counts[b] == len(es), (b, counts[b], len(es))
+        assert (slots[b, :len(es)] == es).all(), (b, slots[b], es)
+        assert (scores[b, :len(es)] == ev).all(), (b, scores[b], ev)   # bit-exact on the ORIGINAL f64 rows
+
+
+def test_keep_f64_is_exact_for_arbitrary_float64_embeddings(rb, oracle_mod):
+    """RBK_INDEX_KEEP_F64: rows that are NOT bf16-representable (what the reference really stores:
+    float64 BLOBs) — ids and fp64 scores still bit-identical to the oracle on the original values."""
+    rng = np.random.default_rng(123)
+    n, d = 30_000, 256
+    corpus = rng.standard_normal((n, d))                       # arbitrary doubles
+    queries = rng.standard_normal((12, d))
+    for i in range(12):                                        # near-duplicates above the 0.5 threshold
+        for j in range(6):
+            corpus[rng.integers(n)] = queries[i] + rng.uniform(0.3, 1.2) * rng.standard_normal(d)
+    corpus[77] = 0.0                                           # zero row -> NaN -> never returned
+    with rb.Index(d, keep_f64=True, capacity_hint=64) as ix:
+        ix.append_f64(corpus[:10_000])
+        ix.append_f32(corpus[10_000:10_500].astype(np.float32))     # f32 rows are widened exactly
+        corpus[10_000:10_500] = corpus[10_000:10_500].astype(np.float32).astype(np.float64)
+        ix.append_f64(corpus[10_500:])
+        check_f64_index(oracle_mod, ix, corpus, queries, 20, 0.5)
+        check_f64_index(oracle_mod, ix, corpus, queries, 20, None)
+        live = np.ones(n, dtype=np.uint8)
+        dead = rng.choice(n, 2000, replace=False)
+        ix.tombstone(dead)
+        live[dead] = 0
+        alive = np.flatnonzero(live)[:20]
+        for s_ in alive:
+            corpus[s_] = rng.standard_normal(d)
+            ix.overwrite_f64(int(s_), corpus[s_])
+        check_f64_index(oracle_mod, ix, corpus, queries, 20, None, live=live)
+        st = ix.stats()
+    # and the same data WITHOUT the sidecar is only bf16-accurate: scores differ from the f64 oracle
+    with rb.Index(d) as ix2:
+        ix2.append_f64(corpus)
+        s2, v2, c2, _ = ix2.search(queries, 5, None)
+        es, ev = oracle_mod.search(corpus, queries[0], 5, None, live=None)
+        assert np.abs(v2[0, :5] - ev).max() < 5e-3 and (v2[0, :5] != ev).any()
+    assert st["queries"] == 36
+
+
 def test_logical_shards_and_merge_kernel(rb, oracle_mod, native):
     """Two shards on one GPU + the merge kernel == one index (the N>1 data path minus NCCL)."""
     import torch
@@ -294,7 +340,11 @@ def test_vector_store_end_to_end_on_gpu(rb, tmp_path):
     from oracle import pyref
     from runbookai_b200 import embedder
     from runbookai_b200.vector_store import VectorStore
-    embedder.configure(HashEmbedder(96))
+    class RawHashEmbedder(HashEmbedder):      # arbitrary float64 vectors, like real embeddings
+        def embed_text(self, text):
+            words = [w for w in text.lower().split() if w]
+            return np.sum([self._word(w) for w in words], axis=0).tolist() if words else [0.0] * self.dim
+    embedder.configure(RawHashEmbedder(96))
     topics = ["redis connection pool exhausted", "kubernetes pod crashloop oom", "postgres replication lag",
               "api gateway latency spike", "certificate expired tls handshake"]
     s = VectorStore(str(tmp_path / "vectors.db"))
