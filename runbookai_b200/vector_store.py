@@ -17,6 +17,7 @@ from __future__ import annotations
 import json
 import os
 import sqlite3
+import threading
 from dataclasses import asdict, dataclass, field
 from typing import Sequence
 
@@ -79,8 +80,10 @@ class VectorStore:
         # CPU stand-in to exercise the host logic where there is no GPU
         # keep_f64: the reference stores float64 embeddings; keep them so the re-rank is exact for any input
         self._index_factory = index_factory or (lambda dim, dev: Index(dim, device=dev, keep_f64=True))
-        self.db = sqlite3.connect(db_path)
+        # one connection, usable from the micro-batcher's worker thread too; serialised by a lock
+        self.db = sqlite3.connect(db_path, check_same_thread=False)
         self.db.row_factory = sqlite3.Row
+        self._db_lock = threading.RLock()
         self.device = int(os.environ.get("RUNBOOK_KNN_DEVICE", "0")) if device is None else device
         self._index: Index | None = None
         self._ids: list[str | None] = []      # slot -> id (None = deleted)
@@ -265,7 +268,8 @@ class VectorStore:
         if type_filter:
             sql += f" AND type IN ({','.join('?' * len(type_filter))})"   # :237-241
             params += list(type_filter)
-        rows = self.db.execute(sql, params).fetchall()
+        with self._db_lock:
+            rows = self.db.execute(sql, params).fetchall()
         score_map = {i: float(s) for i, s in zip(top_ids, scores)}
         results: list[RetrievedChunk] = []
         for row in rows:

@@ -182,3 +182,32 @@ def test_hybrid_retriever_modes_with_cpu_standin(tmp_path, oracle_mod):
     assert set(by_type) == {"runbooks", "postmortems", "architecture", "knownIssues"}
     h.close()
     embedder.reset()
+
+
+def test_micro_batcher_coalesces_and_matches_individual_searches(store):
+    """concurrent search() calls share one device pass and each caller still gets exactly
+    what its own VectorStore.search() returns (own topK, minScore, filters)."""
+    import threading
+    from runbookai_b200.batcher import MicroBatcher
+    store.add_chunks(_chunks(15, "doc1", "runbook", ("api",)))
+    store.add_chunks(_chunks(15, "doc2", "postmortem", ("db",), text="redis connection pool exhausted failover"))
+    store.add_chunks(_chunks(15, "doc3", "runbook", ("web",), text="kubernetes pod crashloop oom"))
+    asks = [("redis connection pool exhausted", {"topK": 5, "minScore": 0.3}),
+            ("pod crashloop oom", {"topK": 3, "minScore": 0.2, "typeFilter": ["runbook"]}),
+            ("redis failover", {"topK": 8, "minScore": 0.25, "serviceFilter": ["db"]}),
+            ("connection pool", {}),
+            ("nothing matches this zzz", {"topK": 4})] * 6
+    want = [store.search(q, o) for q, o in asks]
+    mb = MicroBatcher(store, window_ms=50.0, max_batch=64)
+    got = [None] * len(asks)
+
+    def worker(i):
+        got[i] = mb.search(*asks[i])
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(asks))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    mb.close()
+    assert got == want
+    assert mb.served == len(asks) and mb.batches <= 3        # 30 concurrent calls -> a handful of passes
