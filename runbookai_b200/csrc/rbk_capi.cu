@@ -147,6 +147,8 @@ struct rbk_index {
   DevBuf<long long> o_slots;
   DevBuf<double> o_scores, part_scores;
   DevBuf<float> dbg;
+  DevBuf<unsigned char> o_block;
+  PinBuf<unsigned char> h_block;
   PinBuf<int> h_flags, h_counts;
   PinBuf<long long> h_slots;
   PinBuf<double> h_scores;
@@ -335,7 +337,8 @@ QueryBuffers query_buffers(rbk_index* ix, int q0) {
 
 // Launch the scan (+ optionally finalize) for every sub-batch.  d_q: device queries.
 rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_fetch, double min_score,
-                    long long* d_slots, double* d_scores, int* d_counts, float* dbg, size_t* ev_cursor) {
+                    long long* d_slots, double* d_scores, int* d_counts, int* d_flags, float* dbg,
+                    size_t* ev_cursor) {
   const int kprime = pick_kprime(ix, k_fetch);
   ix->stats.last_kprime = kprime;
   CK(launch_prep_queries(d_q, src_type, B, ix->dim, ix->dpad, min_score,
@@ -348,7 +351,7 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
       CK(cudaMemsetAsync(d_counts, 0, sizeof(int) * B, ix->stream));
       CK(cudaMemsetAsync(d_slots, 0xFF, sizeof(long long) * B * k_fetch, ix->stream));   // -1
       CK(cudaMemsetAsync(d_scores, 0xFF, sizeof(double) * B * k_fetch, ix->stream));     // NaN
-      CK(cudaMemsetAsync(ix->flags.p, 0, sizeof(int) * B, ix->stream));
+      CK(cudaMemsetAsync(d_flags, 0, sizeof(int) * B, ix->stream));
     }
     return RBK_OK;
   }
@@ -429,7 +432,7 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
       fp.out_slots = d_slots + static_cast<size_t>(q0) * k_fetch;
       fp.out_scores = d_scores + static_cast<size_t>(q0) * k_fetch;
       fp.out_counts = d_counts + q0;
-      fp.flags = ix->flags.p + q0;
+      fp.flags = d_flags + q0;
       CK(launch_finalize(fp, ix->stream));
       ix->stats.kernel_launches++;
     }
@@ -493,19 +496,25 @@ rbk_status search_core(rbk_index* ix, const void* q_host, const void* q_dev, int
   rbk_status st = ensure_query_scratch(ix, B, elem);
   if (st != RBK_OK) return st;
   const size_t nout = static_cast<size_t>(B) * k_fetch;
-  if (!d_slots) {
-    CK(ix->o_slots.ensure(nout));
-    CK(ix->o_scores.ensure(nout));
-    CK(ix->o_counts.ensure(B));
-    d_slots = ix->o_slots.p;
-    d_scores = ix->o_scores.p;
-    d_counts = ix->o_counts.p;
-  }
-  CK(ix->h_flags.ensure(B));
-  if (h_slots) {
-    CK(ix->h_slots.ensure(nout));
-    CK(ix->h_scores.ensure(nout));
-    CK(ix->h_counts.ensure(B));
+  // Host-output calls use ONE packed device block (slots | scores | counts | flags) mirrored by one pinned
+  // host block, so results and exactness flags come back in a single D2H copy.
+  const size_t off_scores = nout * 8, off_counts = nout * 16, off_flags = off_counts + static_cast<size_t>(B) * 4;
+  const size_t blk = off_flags + static_cast<size_t>(B) * 4;
+  const bool packed = d_slots == nullptr;
+  int* d_flags = ix->flags.p;
+  const int* h_flags = nullptr;
+  if (packed) {
+    CK(ix->o_block.ensure(blk));
+    CK(ix->h_block.ensure(blk));
+    unsigned char* base = ix->o_block.p;
+    d_slots = reinterpret_cast<long long*>(base);
+    d_scores = reinterpret_cast<double*>(base + off_scores);
+    d_counts = reinterpret_cast<int*>(base + off_counts);
+    d_flags = reinterpret_cast<int*>(base + off_flags);
+    h_flags = reinterpret_cast<const int*>(ix->h_block.p + off_flags);
+  } else {
+    CK(ix->h_flags.ensure(B));
+    h_flags = ix->h_flags.p;
   }
   size_t evc = 2;
   CK(cudaEventRecord(get_event(ix, 0), ix->stream));
@@ -515,27 +524,23 @@ rbk_status search_core(rbk_index* ix, const void* q_host, const void* q_dev, int
                        ix->stream));
     d_q = ix->q_raw.p;
   }
-  st = run_scan(ix, d_q, elem == 8 ? 0 : 1, B, k_fetch, min_score, d_slots, d_scores, d_counts, nullptr, &evc);
+  st = run_scan(ix, d_q, elem == 8 ? 0 : 1, B, k_fetch, min_score, d_slots, d_scores, d_counts, d_flags, nullptr,
+                &evc);
   if (st != RBK_OK) return st;
-  CK(cudaMemcpyAsync(ix->h_flags.p, ix->flags.p, sizeof(int) * B, cudaMemcpyDeviceToHost, ix->stream));
-  auto copy_results = [&]() -> cudaError_t {
-    cudaError_t e;
-    if ((e = cudaMemcpyAsync(ix->h_slots.p, d_slots, sizeof(long long) * nout, cudaMemcpyDeviceToHost, ix->stream)))
-      return e;
-    if ((e = cudaMemcpyAsync(ix->h_scores.p, d_scores, sizeof(double) * nout, cudaMemcpyDeviceToHost, ix->stream)))
-      return e;
-    return cudaMemcpyAsync(ix->h_counts.p, d_counts, sizeof(int) * B, cudaMemcpyDeviceToHost, ix->stream);
+  auto copy_back = [&]() -> cudaError_t {
+    if (packed) return cudaMemcpyAsync(ix->h_block.p, ix->o_block.p, blk, cudaMemcpyDeviceToHost, ix->stream);
+    return cudaMemcpyAsync(ix->h_flags.p, d_flags, sizeof(int) * B, cudaMemcpyDeviceToHost, ix->stream);
   };
-  if (h_slots) CK(copy_results());
+  CK(copy_back());
   CK(cudaEventRecord(get_event(ix, 1), ix->stream));
   CK(cudaStreamSynchronize(ix->stream));
   std::vector<int> fails;
   for (int b = 0; b < B; ++b)
-    if (ix->h_flags.p[b]) fails.push_back(b);
+    if (h_flags[b]) fails.push_back(b);
   if (!fails.empty()) {
     st = run_fallback(ix, fails, k_fetch, min_score, d_slots, d_scores, d_counts);
     if (st != RBK_OK) return st;
-    if (h_slots) CK(copy_results());
+    if (packed) CK(copy_back());
     CK(cudaEventRecord(get_event(ix, 1), ix->stream));
     CK(cudaStreamSynchronize(ix->stream));
   }
@@ -551,9 +556,9 @@ rbk_status search_core(rbk_index* ix, const void* q_host, const void* q_dev, int
   ix->stats.queries += B;
   if (ms_out) *ms_out = total;
   if (h_slots) {
-    memcpy(h_slots, ix->h_slots.p, sizeof(int64_t) * nout);
-    memcpy(h_scores, ix->h_scores.p, sizeof(double) * nout);
-    memcpy(h_counts, ix->h_counts.p, sizeof(int32_t) * B);
+    memcpy(h_slots, ix->h_block.p, sizeof(int64_t) * nout);
+    memcpy(h_scores, ix->h_block.p + off_scores, sizeof(double) * nout);
+    memcpy(h_counts, ix->h_block.p + off_counts, sizeof(int32_t) * B);
   }
   return RBK_OK;
 }
@@ -658,6 +663,8 @@ void rbk_index_destroy(rbk_index* ix) {
     ix->o_scores.release();
     ix->part_scores.release();
     ix->dbg.release();
+    ix->o_block.release();
+    ix->h_block.release();
     ix->h_flags.release();
     ix->h_counts.release();
     ix->h_slots.release();
@@ -851,7 +858,7 @@ rbk_status rbk_index_debug_scores_f32(rbk_index* ix, const float* queries, int32
   CK(cudaMemsetAsync(ix->dbg.p, 0xFF, n * 4, ix->stream));
   CK(cudaMemcpyAsync(ix->q_raw.p, queries, static_cast<size_t>(B) * ix->dim * 4, cudaMemcpyHostToDevice, ix->stream));
   size_t evc = 2;
-  st = run_scan(ix, ix->q_raw.p, 1, B, 16, -INFINITY, nullptr, nullptr, nullptr, ix->dbg.p, &evc);
+  st = run_scan(ix, ix->q_raw.p, 1, B, 16, -INFINITY, nullptr, nullptr, nullptr, nullptr, ix->dbg.p, &evc);
   if (st != RBK_OK) return st;
   std::vector<float> invq(B);
   CK(cudaMemcpyAsync(out_scores, ix->dbg.p, n * 4, cudaMemcpyDeviceToHost, ix->stream));

@@ -362,6 +362,11 @@ def test_vector_store_end_to_end_on_gpu(rb, tmp_path):
         assert [f"vec_{r.id}" for r in got] == [i for i, _ in ref]
         assert [r.score for r in got] == [sc for _, sc in ref]
         assert got == s.search(q, {"topK": 7, "minScore": 0.2})
+    from runbookai_b200.batcher import MicroBatcher                 # SURVEY 8f-3 on the real device index
+    mb = MicroBatcher(s, window_ms=20.0)
+    futs = [mb.submit(q, {"topK": 7, "minScore": 0.2}) for q in qs]
+    assert [f.result(timeout=30) for f in futs] == batch
+    mb.close()
     s.delete_document("doc0")
     assert all(r.documentId != "doc0" for r in s.search(qs[0], {"topK": 7, "minScore": 0.2}))
     s.close()
