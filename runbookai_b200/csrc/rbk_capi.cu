@@ -155,6 +155,7 @@ struct rbk_index {
   PinBuf<float> h_f32;
   CUtensorMap tmap_c, tmap_c_half, tmap_c_half32, tmap_c_pf, tmap_c_r32;
   int perf_probe = 0;
+  int max_lead_tiles = kMaxLeadTiles;
   int hybrid_res_kb = -1, hybrid_slots = 8;   // -1: hybrid pair kernel off
   bool use_ts = false;  // pair kernel with queries in TMEM (dim <= 768): correct but not yet faster
   bool force_1cta = false, force_streamed = true;   // query-resident pair kernel: measured slower
@@ -397,6 +398,7 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
     const bool resident = pairs && !ix->force_streamed && scan2_resident_fits(ix->dpad);
     sp.prefetch_tiles = ix->prefetch_tiles;
     sp.perf_probe = ix->perf_probe;
+    sp.max_lead_tiles = ix->max_lead_tiles;
     const bool ts = pairs && ix->use_ts && scan3_fits(ix->dpad);
     if (pairs && !ts && ix->hybrid_res_kb >= 0)
       CK(launch_scan2h(tmap_q, ix->tmap_c_half, sp, ix->hybrid_res_kb, ix->hybrid_slots, ix->stream));
@@ -604,6 +606,7 @@ rbk_status rbk_index_create_ex(int32_t dim, int32_t device, int64_t capacity_hin
   if (const char* m = getenv("RBK_KNN_FORCE_1CTA")) ix->force_1cta = atoi(m) != 0;   // A/B measurements only
   if (const char* m = getenv("RBK_KNN_RESIDENT")) ix->force_streamed = atoi(m) == 0;   // experiments only
   if (const char* m = getenv("RBK_KNN_TS")) ix->use_ts = atoi(m) != 0;
+  if (const char* m = getenv("RBK_KNN_MAX_LEAD")) ix->max_lead_tiles = std::max(1, atoi(m));
   if (const char* m = getenv("RBK_KNN_PERF_PROBE")) ix->perf_probe = atoi(m);   // breaks results; timing only
   if (const char* m = getenv("RBK_KNN_HYBRID_KB")) ix->hybrid_res_kb = atoi(m);
   if (const char* m = getenv("RBK_KNN_HYBRID_SLOTS")) ix->hybrid_slots = atoi(m);

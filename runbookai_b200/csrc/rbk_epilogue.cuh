@@ -315,13 +315,13 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
 // Bounded-lag lockstep of the QB producers that stream the same corpus range: nobody runs
 // more than kMaxLeadTiles ahead of the slowest, so a tile pulled from HBM by the first
 // reader is still in L2 for the others (keeps DRAM traffic close to 1x the corpus).
-__device__ __forceinline__ void lockstep_pace(volatile int* prog, int QB, int qb, int it) {
+__device__ __forceinline__ void lockstep_pace(volatile int* prog, int QB, int qb, int it, int max_lead) {
   if (QB <= 1 || (it & 1) != 0) return;
   prog[qb] = it;
   for (int o = 0; o < QB; ++o) {
     if (o == qb) continue;
     const long long w0 = clock64();
-    while (prog[o] < it - kMaxLeadTiles) {
+    while (prog[o] < it - max_lead) {
       __nanosleep(200);
       if (clock64() - w0 > (1ll << 24)) break;   // a pacing hint, never a correctness wait
     }

@@ -82,7 +82,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
     int s = 0;
     uint32_t ph = 0;
     for (int tile = t0; tile < t1; ++tile) {
-      if (lane == 0) lockstep_pace(prog, p.QB, qb, tile - t0);
+      if (lane == 0) lockstep_pace(prog, p.QB, qb, tile - t0, p.max_lead_tiles);
       __syncwarp();
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(smem_u32(&tail->empty[s]), ph ^ 1u);

@@ -8,7 +8,7 @@
 // CTA stages 128 corpus rows and its own 128 queries; the UMMA reads both halves).
 //
 //   scan2_kernel<false>  "streamed":  queries and corpus both flow through the smem ring
-//                         (6 stages x 32 KB, K=64, 128-byte swizzle).  Any dim.
+//                         (7 stages x 32 KB, K=64, 128-byte swizzle).  Any dim.
 //                         L2->SM bytes per 256 q x 256 rows: 786 KB.
 //   scan2_kernel<true>   "resident":  dim <= 768: the CTA's 128 queries stay in smem for the
 //                         whole kernel (<= 12 panels x 16 KB, 128-byte swizzle) and only the
@@ -32,11 +32,14 @@ namespace {
 
 constexpr int kHalfN = kBlockN / 2;                  // corpus rows staged per CTA
 constexpr int kTmemCols = 512;
-constexpr int kMaxStages2 = 6;
+constexpr int kMaxStages2 = 7;
 constexpr int kPanelBytes = kBlockM * kBlockK * 2;   // 16 KiB: 128 rows x 64 bf16, SWIZZLE_128B
 
 // streamed variant
-constexpr int kStagesS = 6;
+#ifndef RBK_STAGES_S
+#define RBK_STAGES_S 7
+#endif
+constexpr int kStagesS = RBK_STAGES_S;
 constexpr int kStageSBytes = kPanelBytes + kHalfN * kBlockK * 2;   // 32 KiB: query slab + corpus half-slab
 // resident variant
 #ifndef RBK_RES_K
@@ -74,7 +77,15 @@ scan2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
-  if (kRes && pad != 0) __trap();   // the resident layout has no slack: the base must be 1024-aligned
+  {
+    // the launch adds 1 KB of alignment slack only when it fits under the 227 KB limit; without slack the
+    // (in practice always 1024-aligned) dynamic smem base must really be aligned
+    uint32_t dyn;
+    asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+    const uint32_t need = (kRes ? static_cast<uint32_t>(p.num_kb) * kPanelBytes + kStagesR * kStageRBytes
+                                : static_cast<uint32_t>(kStagesS) * kStageSBytes) + static_cast<uint32_t>(sizeof(SmemTail2));
+    if (pad + need > dyn) __trap();
+  }
   uint8_t* smem = smem_raw + pad;
   const uint32_t smem_base = smem_u32(smem);
   constexpr int kStages = kRes ? kStagesR : kStagesS;
@@ -135,7 +146,7 @@ scan2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     int s = 0;
     uint32_t ph = 0;
     for (int tile = t0; tile < t1; ++tile) {
-      if (rank == 0 && lane == 0) lockstep_pace(prog, p.QB, qb, tile - t0);
+      if (rank == 0 && lane == 0) lockstep_pace(prog, p.QB, qb, tile - t0, p.max_lead_tiles);
       __syncwarp();
       const int c_row0 = tile * kBlockN + static_cast<int>(rank) * kHalfN;
       if (kRes && p.prefetch_tiles > 0 && tile + p.prefetch_tiles < t1 && lane == 0) {
@@ -311,7 +322,7 @@ scan2h_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     int s = 0;
     uint32_t ph = 0;
     for (int tile = t0; tile < t1; ++tile) {
-      if (rank == 0 && lane == 0) lockstep_pace(prog, p.QB, qb, tile - t0);
+      if (rank == 0 && lane == 0) lockstep_pace(prog, p.QB, qb, tile - t0, p.max_lead_tiles);
       __syncwarp();
       const int c_row0 = tile * kBlockN + static_cast<int>(rank) * kHalfN;
       for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -410,7 +421,8 @@ cudaError_t launch_scan2(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, c
     if (e != cudaSuccess) return e;
     scan2_kernel<true><<<2 * p.QB * p.R, kScanThreads, smem, stream>>>(tmap_q, tmap_c, tmap_pf, p);
   } else {
-    const size_t smem = static_cast<size_t>(kStagesS) * kStageSBytes + sizeof(SmemTail2) + 1024;
+    size_t smem = static_cast<size_t>(kStagesS) * kStageSBytes + sizeof(SmemTail2);
+    if (smem + 1024 <= kMaxSmem) smem += 1024;   // alignment slack when there is room
     e = cudaFuncSetAttribute(scan2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     scan2_kernel<false><<<2 * p.QB * p.R, kScanThreads, smem, stream>>>(tmap_q, tmap_c, tmap_pf, p);

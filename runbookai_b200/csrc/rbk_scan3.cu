@@ -125,7 +125,7 @@ scan3_kernel(const __grid_constant__ CUtensorMap tmap_c, const ScanParams p, con
     int s = 0;
     uint32_t ph = 0;
     for (int tile = t0; tile < t1; ++tile) {
-      if (rank == 0 && lane == 0) lockstep_pace(prog, p.QB, qb, tile - t0);
+      if (rank == 0 && lane == 0) lockstep_pace(prog, p.QB, qb, tile - t0, p.max_lead_tiles);
       __syncwarp();
       for (int j = 0; j < kSubPerTile; ++j) {
         const int c_row0 = tile * kBlockN + j * kSubN + static_cast<int>(rank) * kSubHalf;
