@@ -73,7 +73,7 @@ __device__ __forceinline__ uint64_t make_sw64_kmajor_desc(uint32_t smem_addr) {
 template <bool kRes>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kScanThreads, 1)
 scan2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
-             const __grid_constant__ CUtensorMap tmap_pf, const ScanParams p) {
+             const __grid_constant__ CUtensorMap tmap_pf, const ScanParams p, const int n_stages_s) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
@@ -83,12 +83,12 @@ scan2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     uint32_t dyn;
     asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
     const uint32_t need = (kRes ? static_cast<uint32_t>(p.num_kb) * kPanelBytes + kStagesR * kStageRBytes
-                                : static_cast<uint32_t>(kStagesS) * kStageSBytes) + static_cast<uint32_t>(sizeof(SmemTail2));
+                                : static_cast<uint32_t>(n_stages_s) * kStageSBytes) + static_cast<uint32_t>(sizeof(SmemTail2));
     if (pad + need > dyn) __trap();
   }
   uint8_t* smem = smem_raw + pad;
   const uint32_t smem_base = smem_u32(smem);
-  constexpr int kStages = kRes ? kStagesR : kStagesS;
+  const int kStages = kRes ? kStagesR : n_stages_s;   // streamed: 7 when the smem base is 1024-aligned, else 6 + slack
   constexpr int kStageBytes = kRes ? kStageRBytes : kStageSBytes;
   // resident: [A panels: num_kb x 16 KB][corpus ring][tail]; streamed: [ring][tail]
   const uint32_t ring_off = kRes ? static_cast<uint32_t>(p.num_kb) * kPanelBytes : 0u;
@@ -241,6 +241,33 @@ scan2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
 }
 
 constexpr size_t kMaxSmem = 232448;   // 227 KiB opt-in limit per CTA on sm_100
+
+__global__ void smem_align_probe_kernel(unsigned int* out) {
+  extern __shared__ __align__(1024) uint8_t probe_smem[];
+  if (threadIdx.x == 0) *out = smem_u32(probe_smem) & 1023u;
+}
+
+// Is the dynamic shared memory window 1024-byte aligned for a near-maximal allocation?  (It is on every
+// driver seen so far; the answer is cached per device.)
+bool smem_base_is_aligned() {
+  static int cached[64];   // 0 = unknown, 1 = aligned, 2 = not
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+  if (cached[dev] == 0) {
+    unsigned int* d = nullptr;
+    unsigned int h = 1;
+    const int smem = 200 * 1024;
+    if (cudaMalloc(reinterpret_cast<void**>(&d), 4) == cudaSuccess &&
+        cudaFuncSetAttribute(smem_align_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) ==
+            cudaSuccess) {
+      smem_align_probe_kernel<<<1, 32, smem>>>(d);
+      if (cudaMemcpy(&h, d, 4, cudaMemcpyDeviceToHost) != cudaSuccess) h = 1;
+    }
+    cudaFree(d);
+    cached[dev] = h == 0 ? 1 : 2;
+  }
+  return cached[dev] == 1;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Hybrid variant: the first `res_kb` 64-column panels of the CTA's queries stay resident in smem,
@@ -414,18 +441,22 @@ bool scan2_resident_fits(int dpad) {
 cudaError_t launch_scan2(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const CUtensorMap& tmap_pf,
                          const ScanParams& p, bool resident, cudaStream_t stream) {
   cudaError_t e;
+  int n_stages = kStagesS;
   if (resident) {
     const size_t smem = static_cast<size_t>(p.num_kb) * kPanelBytes + static_cast<size_t>(kStagesR) * kStageRBytes +
                         sizeof(SmemTail2);
     e = cudaFuncSetAttribute(scan2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    scan2_kernel<true><<<2 * p.QB * p.R, kScanThreads, smem, stream>>>(tmap_q, tmap_c, tmap_pf, p);
+    scan2_kernel<true><<<2 * p.QB * p.R, kScanThreads, smem, stream>>>(tmap_q, tmap_c, tmap_pf, p, n_stages);
   } else {
-    size_t smem = static_cast<size_t>(kStagesS) * kStageSBytes + sizeof(SmemTail2);
-    if (smem + 1024 <= kMaxSmem) smem += 1024;   // alignment slack when there is room
+    // 7 stages fill the 227 KB exactly (no alignment slack): only when the dynamic smem base is 1024-aligned on
+    // this device/driver (probed once); otherwise 6 stages + 1 KB of slack
+    n_stages = smem_base_is_aligned() ? kStagesS : kStagesS - 1;
+    size_t smem = static_cast<size_t>(n_stages) * kStageSBytes + sizeof(SmemTail2);
+    if (smem + 1024 <= kMaxSmem) smem += 1024;
     e = cudaFuncSetAttribute(scan2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    scan2_kernel<false><<<2 * p.QB * p.R, kScanThreads, smem, stream>>>(tmap_q, tmap_c, tmap_pf, p);
+    scan2_kernel<false><<<2 * p.QB * p.R, kScanThreads, smem, stream>>>(tmap_q, tmap_c, tmap_pf, p, n_stages);
   }
   return cudaGetLastError();
 }
