@@ -149,6 +149,8 @@ typedef struct {
   float last_total_ms;      /* device time of the whole last search */
   int32_t last_kprime;      /* candidates kept per query by the last scan */
   int32_t sm_count;
+  int32_t last_ring_stages; /* smem ring depth of the last scan kernel (pair kernel: 7, or 6 if the smem base is unaligned) */
+  int32_t reserved;
 } rbk_stats;
 rbk_status rbk_index_stats(const rbk_index* idx, rbk_stats* out);
 

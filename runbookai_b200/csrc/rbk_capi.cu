@@ -406,7 +406,7 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
       CK(launch_scan3(ix->tmap_c_r32, sp, ix->q_bf16.p + static_cast<size_t>(q0) * ix->dpad, ix->stream));
     else if (pairs)
       CK(launch_scan2(tmap_q, (resident && scan2_resident_k() == 32) ? ix->tmap_c_half32 : ix->tmap_c_half,
-                      ix->tmap_c_pf, sp, resident, ix->stream));
+                      ix->tmap_c_pf, sp, resident, ix->stream, &ix->stats.last_ring_stages));
     else CK(launch_scan(tmap_q, ix->tmap_c, sp, ix->stream));
     CK(cudaEventRecord(get_event(ix, (*ev_cursor)++), ix->stream));
     ix->stats.scan_launches++;

@@ -316,7 +316,7 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
 // more than kMaxLeadTiles ahead of the slowest, so a tile pulled from HBM by the first
 // reader is still in L2 for the others (keeps DRAM traffic close to 1x the corpus).
 __device__ __forceinline__ void lockstep_pace(volatile int* prog, int QB, int qb, int it, int max_lead) {
-  if (QB <= 1 || (it & 1) != 0) return;
+  if (QB <= 1 || (it & 1) != 0) return;   // every other tile: checking every tile costs ~10 % on short kernels
   prog[qb] = it;
   for (int o = 0; o < QB; ++o) {
     if (o == qb) continue;

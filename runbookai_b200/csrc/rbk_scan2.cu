@@ -439,7 +439,7 @@ bool scan2_resident_fits(int dpad) {
 // streamed: tmap_c has 128-row x 64-col boxes (SWIZZLE_128B); resident: the same, or 128-row x 32-col
 // (SWIZZLE_64B) when built with RBK_RES_K=32.
 cudaError_t launch_scan2(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const CUtensorMap& tmap_pf,
-                         const ScanParams& p, bool resident, cudaStream_t stream) {
+                         const ScanParams& p, bool resident, cudaStream_t stream, int* ring_stages_out) {
   cudaError_t e;
   int n_stages = kStagesS;
   if (resident) {
@@ -457,6 +457,7 @@ cudaError_t launch_scan2(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, c
     e = cudaFuncSetAttribute(scan2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     scan2_kernel<false><<<2 * p.QB * p.R, kScanThreads, smem, stream>>>(tmap_q, tmap_c, tmap_pf, p, n_stages);
+    if (ring_stages_out) *ring_stages_out = n_stages;
   }
   return cudaGetLastError();
 }

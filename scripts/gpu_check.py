@@ -96,6 +96,7 @@ def stage_time(n=1_000_000, d=768, b=256, k=32, iters=5, tag="time"):
     emit(tag, n=n, d=d, b=b, k=k, total_ms=[round(r[0], 3) for r in res], scan_ms=[round(r[1], 3) for r in res],
          qps_scan=b / (best_scan * 1e-3), tflops=2.0 * b * n * d / (best_scan * 1e-3) / 1e12,
          gbps=2.0 * n * d / (best_scan * 1e-3) / 1e9, fallback=ix.stats()["fallback_queries"],
+         ring=ix.stats()["last_ring_stages"],
          counts=counts[:4].tolist())
     ix.close()
 
