@@ -70,7 +70,15 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.monotonic()] + [x.strip() for x in line.split(",")])
+
+    def window(self, t0: float, t1: float):
+        """Keep only the samples taken inside [t0, t1] (monotonic clock); if the window was shorter than the
+        sampling period, the sample nearest to it."""
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        if not inside and self.rows:
+            inside = [min(self.rows, key=lambda r: min(abs(r[0] - t0), abs(r[0] - t1)))]
+        self.rows = inside
 
     def stop(self):
         if self.proc:
@@ -79,8 +87,10 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        rows = [r[1:] for r in self.rows]   # drop the timestamp
+        self.rows = rows
+        sm = [float(r[1]) for r in rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
         reasons = []
         for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6),
                           ("sw_power_cap", 7)):
@@ -187,6 +197,9 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()   # nvidia-smi takes a second to start: launch it now, keep only the timed region's samples
     lo, hi = shard_bounds(n, world, rank)
     ix = Index(d, device=local, capacity_hint=hi - lo)
     ix.set_slot_base(lo)
@@ -205,14 +218,11 @@ def main():
         torch.cuda.synchronize(device)
 
     # ---------------- value: batch resident in HBM ----------------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()          # nvidia-smi needs a moment to start: launch it before the warm-up
     for _ in range(args.warmup):
         searcher.search_device(q_dev, k_fetch, None)
     launches0 = ix.stats()["kernel_launches"]
     barrier()
-    sampler.rows.clear()         # keep only samples taken inside the timed region
+    t_region0 = time.monotonic()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scan_ms = []
     ev0.record(stream)
@@ -227,8 +237,10 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    if rank == 0 and not sampler.rows:
-        time.sleep(0.08)   # a very short timed region can fall between two nvidia-smi samples: take the next one
+    if rank == 0:
+        t_region1 = time.monotonic()
+        time.sleep(0.05)   # let the last sample of the region arrive
+        sampler.window(t_region0, t_region1)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- e2e: host buffers through the public call ----------------
