@@ -172,8 +172,8 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p)
   __shared__ double s_score[kMaxKPrime];
   __shared__ int s_row[kMaxKPrime];
   __shared__ int s_valid[kMaxKPrime];
-  __shared__ int s_total, s_nsel, s_nvalid, s_bin, s_want;
-  __shared__ unsigned long long s_prefix;
+  __shared__ int s_total, s_nsel, s_nvalid, s_bin, s_want, s_done;
+  __shared__ unsigned long long s_prefix, s_minkey;
   __shared__ double s_ekth;
 
   if (tid == 0) {
@@ -181,6 +181,8 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p)
     s_nsel = 0;
     s_nvalid = 0;
     s_ekth = 0.0;
+    s_done = 0;
+    s_minkey = ~0ull;
   }
   __syncthreads();
   int local = 0;
@@ -221,16 +223,30 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p)
       }
     }
     __syncthreads();
-    for (int i = tid; i < M; i += kFinThreads) {
-      int lo = 0, hi = p.R - 1;   // last r with s_off[r] <= i
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (s_off[mid] <= i) lo = mid;
-        else hi = mid - 1;
+    // four independent loads in flight per thread (a load -> store loop exposes one L2 round trip per key)
+    for (int i0 = tid; i0 < M; i0 += 4 * kFinThreads) {
+      unsigned long long kv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kFinThreads;
+        kv[u] = 0ull;
+        if (i < M) {
+          int lo = 0, hi = p.R - 1;   // last r with s_off[r] <= i
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_off[mid] <= i) lo = mid;
+            else hi = mid - 1;
+          }
+          const unsigned long long* l =
+              p.cand + (static_cast<size_t>(qb * p.R + lo) * p.block_m + qrow) * static_cast<size_t>(kListCap);
+          kv[u] = __ldcg(l + (i - s_off[lo]));
+        }
       }
-      const unsigned long long* l =
-          p.cand + (static_cast<size_t>(qb * p.R + lo) * p.block_m + qrow) * static_cast<size_t>(kListCap);
-      s_keys[i] = __ldcg(l + (i - s_off[lo]));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kFinThreads;
+        if (i < M) s_keys[i] = kv[u];
+      }
     }
     __syncthreads();
   }
@@ -276,12 +292,15 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p)
           }
           s_bin = b;
           s_want = static_cast<int>(want - cum);
+          // every key left in this bin is wanted: the bin's lower edge is already a valid pivot
+          s_done = (s_hist[b] == want - cum) ? 1 : 0;
         }
       }
       __syncthreads();
       if (tid == 0) s_prefix = prefix | (static_cast<unsigned long long>(s_bin) << shift);
       mask |= 0xFFull << shift;
       __syncthreads();
+      if (s_done) break;   // uniform: read after the barrier
     }
     pivot = s_prefix;
   }
@@ -289,12 +308,13 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p)
     if (k >= pivot) {
       const int pos = atomicAdd(&s_nsel, 1);
       if (pos < kMaxKPrime) s_sel[pos] = k;
+      atomicMin(&s_minkey, k);   // the k'-th best key itself (the pivot may be only a bin edge after an early exit)
     }
   });
   __syncthreads();
   const int nsel = s_nsel < kMaxKPrime ? s_nsel : kMaxKPrime;
   // every row that is NOT a candidate has raw score <= tau_raw (or was cut by thr_init)
-  const float tau_raw = M >= kprime ? key_score(pivot) : -INFINITY;
+  const float tau_raw = M >= kprime ? key_score(s_minkey) : -INFINITY;
 
   // ---- K4: exact fp64 re-score of the candidates ----
   // The arithmetic is a sequential chain per candidate (parity contract), so global-load latency
@@ -317,11 +337,26 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p)
       const int len = p.d - c0 < chunk ? p.d - c0 : chunk;            // elements of this chunk
       const int len16 = (len + 7) >> 3;                               // rows are zero padded to dpad (multiple of 8)
       __syncthreads();                                                // previous chunk fully consumed
-      for (int i = tid; i < nsel * len16; i += kFinThreads) {
-        const int rr = i / len16, u = i - rr * len16;
-        const int row = static_cast<int>(key_row(s_sel[rr]));
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.rows + static_cast<size_t>(row) * p.dpad + c0) + u);
-        *reinterpret_cast<uint4*>(s_rows + rr * row_stride + u * 16) = v;
+      for (int i0 = tid; i0 < nsel * len16; i0 += 4 * kFinThreads) {   // 4 row pieces in flight per thread
+        uint4 pv[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int i = i0 + b * kFinThreads;
+          pv[b] = make_uint4(0u, 0u, 0u, 0u);
+          if (i < nsel * len16) {
+            const int rr = i / len16, u = i - rr * len16;
+            const int row = static_cast<int>(key_row(s_sel[rr]));
+            pv[b] = __ldg(reinterpret_cast<const uint4*>(p.rows + static_cast<size_t>(row) * p.dpad + c0) + u);
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int i = i0 + b * kFinThreads;
+          if (i < nsel * len16) {
+            const int rr = i / len16, u = i - rr * len16;
+            *reinterpret_cast<uint4*>(s_rows + rr * row_stride + u * 16) = pv[b];
+          }
+        }
       }
       for (int i = tid; i < len; i += kFinThreads) s_q[i] = __ldg(qv + c0 + i);
       __syncthreads();
