@@ -320,8 +320,9 @@ rbk_status ensure_query_scratch(rbk_index* ix, int B, int elem) {
   CK(ix->flags.ensure(B));
   CK(ix->cand.ensure(static_cast<size_t>(ix->sm_count) * kBlockM * kListCap));
   CK(ix->cand_cnt.ensure(static_cast<size_t>(ix->sm_count) * kBlockM));
-  // hist [kMaxSubBatch][kHistBins] | maxbin [kMaxSubBatch] | progress [sm_count + 8]: one buffer, one memset
-  CK(ix->hist.ensure(static_cast<size_t>(kMaxSubBatch) * kHistBins + kMaxSubBatch + ix->sm_count + 8));
+  // hist [kMaxSubBatch][kHistBins] | maxbin [kMaxSubBatch] | gthr [kMaxSubBatch] | progress [sm_count + 8]:
+  // one buffer, one memset
+  CK(ix->hist.ensure(static_cast<size_t>(kMaxSubBatch) * kHistBins + 2 * kMaxSubBatch + ix->sm_count + 8));
   return RBK_OK;
 }
 
@@ -375,12 +376,14 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
     sp.thr_init = ix->thr_init.p + q0;
     sp.inv_norm_q = ix->q_inv_norm.p + q0;
     {
-      // per-launch scratch, zeroed with one memset: hist rows of this sub-batch, then maxbin, then progress
+      // per-launch scratch, zeroed with one memset: hist rows of this sub-batch, then maxbin, gthr, progress
       unsigned int* base = ix->hist.p;
       sp.hist = base;
       sp.maxbin = reinterpret_cast<int*>(base + static_cast<size_t>(Bs) * kHistBins);
-      sp.progress = sp.maxbin + Bs;
-      CK(cudaMemsetAsync(base, 0, sizeof(unsigned int) * (static_cast<size_t>(Bs) * kHistBins + Bs + ix->sm_count + 8),
+      sp.gthr = reinterpret_cast<unsigned int*>(sp.maxbin + Bs);
+      sp.progress = sp.maxbin + 2 * Bs;
+      CK(cudaMemsetAsync(base, 0,
+                         sizeof(unsigned int) * (static_cast<size_t>(Bs) * kHistBins + 2 * Bs + ix->sm_count + 8),
                          ix->stream));
     }
     sp.cand = ix->cand.p;

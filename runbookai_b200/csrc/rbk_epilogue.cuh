@@ -24,6 +24,7 @@ struct FilterState {
   int mb_cache;    // highest bin this thread already published to maxbin
   int cnt;         // entries in the list
   bool valid;
+  int probe;       // timing experiments only (ScanParams::perf_probe)
   unsigned long long* list;
   unsigned int* hist_q;  // [kHistBins]
   int* maxbin_q;
@@ -48,6 +49,7 @@ __device__ __forceinline__ void filter_init(FilterState& s, bool valid, float th
   s.qn = s.valid ? 1.0f / inv_q : 0.f;
   s.tb = (s.valid && thr_init > -INFINITY) ? score_bin(thr_init * inv_q) : -1;
   s.mb_cache = -1;
+  s.probe = 0;
   s.cnt = 0;
   s.list = list;
   s.hist_q = hist_q;
@@ -58,7 +60,7 @@ __device__ __forceinline__ void filter_init(FilterState& s, bool valid, float th
 // Bins are fetched 16 at a time (four independent 16-byte L2 loads in flight): a dependent chain
 // of single loads cost ~0.7 us per 4 bins and made this function 23 % of the epilogue's time.
 static __device__ __noinline__ void filter_refresh(FilterState& s, int kprime) {
-  if (!s.valid) return;
+  if (!s.valid || s.probe == 3) return;
   const int mb = __ldcg(s.maxbin_q);
   if (mb <= s.tb) return;
   const uint4* h4 = reinterpret_cast<const uint4*>(s.hist_q);
@@ -93,10 +95,29 @@ static __device__ __noinline__ void filter_refresh(FilterState& s, int kprime) {
 __device__ __forceinline__ bool refresh_due(int it) {
   return it != 0 && (it < 8 || (it < 64 && (it & 7) == 0) || (it & 31) == 0);
 }
+// Shared-threshold variant (run_epilogue): walking the histogram costs a thread ~3 us, during which its
+// accumulator stage is not drained.  The R units that scan different corpus ranges for the same queries
+// would all compute the same number, so they take turns: at step `it` only unit it % R walks the histogram
+// and publishes the result in gthr[q]; everybody else picks it up with one (prefetched) load per tile.
+// The duty being spread over R units, it can come round far more often than a private refresh could.
+__device__ __forceinline__ bool publish_due(int it) {
+  return it != 0 && (it < 16 || (it < 64 && (it & 1) == 0) || (it & 7) == 0);
+}
+__device__ __forceinline__ void publish_threshold(FilterState& s, unsigned int* gthr_q, int kprime) {
+  if (!s.valid) return;
+  // thr may have been adopted from gthr since this thread last walked the histogram: skip the bins below it
+  s.tb = max(s.tb, score_bin(s.thr * s.inv_q) - 1);
+  filter_refresh(s, kprime);
+  if (s.thr > -INFINITY) atomicMax(gthr_q, f32_ordered(s.thr));
+}
+__device__ __forceinline__ void adopt_threshold(FilterState& s, unsigned int ordered) {
+  s.thr = fmaxf(s.thr, f32_from_ordered(ordered));   // 0 (nothing published) decodes to NaN, which fmaxf drops
+}
 
 __device__ __forceinline__ void filter_append(FilterState& s, float t, uint32_t row) {
   s.list[s.cnt] = pack_key(t, row);
   ++s.cnt;
+  if (s.probe == 3) return;   // probe: no histogram
   const int b = score_bin(t * s.inv_q);
   atomicAdd(s.hist_q + b, 1u);
   if (b > s.mb_cache) {
@@ -120,6 +141,10 @@ __device__ __forceinline__ void filter_chunk(FilterState& s, const uint32_t (&v)
     const float a3 = __uint_as_float(v[4 * j + 3]) * w.w;
     g[j] = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));   // fmaxf drops NaN (dead / out-of-range rows)
     m = fmaxf(m, g[j]);
+  }
+  if (s.probe == 2) {   // probe: fast path only
+    if (m == 12345.678f) s.cnt = 1;
+    return;
   }
   if (m > s.thr) {
     // Rare per LANE but not per WARP while thresholds are still converging (1024 (query,row) pairs per warp
@@ -245,10 +270,13 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
   filter_init(fs, q_valid, q_valid ? p.thr_init[q] : INFINITY, q_valid ? p.inv_norm_q[q] : 0.f,
               p.cand + (static_cast<size_t>(qb * p.R + r) * kBlockQ + qin) * static_cast<size_t>(kListCap),
               p.hist + static_cast<size_t>(q_valid ? q : 0) * kHistBins, p.maxbin + (q_valid ? q : 0));
+  fs.probe = p.perf_probe;
   int as = 0;
   uint32_t aph = 0;
   // the next tile's 1/||c|| travels in registers while this tile is processed (hides its L2/HBM latency)
   float nx0 = 0.f, nx1 = 0.f;
+  unsigned int* gthr_q = p.gthr + (q_valid ? q : 0);
+  unsigned int ngt = 0u;   // published threshold, fetched one tile ahead like the norms
   if (t0 < t1) {
     nx0 = __ldg(p.inv_norm_c + t0 * kBlockN + et);
     nx1 = __ldg(p.inv_norm_c + t0 * kBlockN + kEpi + et);
@@ -263,8 +291,10 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
       nx0 = __ldg(p.inv_norm_c + (tile + 1) * kBlockN + et);
       nx1 = __ldg(p.inv_norm_c + (tile + 1) * kBlockN + kEpi + et);
     }
+    adopt_threshold(fs, ngt);
+    ngt = __ldcg(gthr_q);
     named_bar_sync(1, kEpi);
-    if (refresh_due(it)) filter_refresh(fs, p.kprime);   // overlaps this tile's MMAs
+    if (publish_due(it) && r == it % p.R) publish_threshold(fs, gthr_q, p.kprime);   // overlaps this tile's MMAs
     mbar_wait(smem_u32(&tmem_full[as]), aph);
     tc_fence_after();
     // Two chunks in flight: the TMEM load of the next 32 columns is issued before the current 32 are
@@ -297,8 +327,10 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
       if (c2 + 1 < kBlockN / 64) tmem_ld_32x32b_x32(tcol + static_cast<uint32_t>((2 * c2 + 2) * 32), va);
       process(vb, 2 * c2 + 1);
       filter_compact_if_needed(fs, p.kprime, lane, 64);
-      if (it == 0 && t1 - t0 > 2) filter_refresh(fs, p.kprime);   // start-up: converge within the first tile
-                                                                  // (pointless when the CTA owns a tile or two)
+      if (it == 0 && t1 - t0 > 2) {   // start-up: converge within the first tile (pointless for a tile or two)
+        if (r == c2 % p.R) publish_threshold(fs, gthr_q, p.kprime);
+        else adopt_threshold(fs, __ldcg(gthr_q));
+      }
     }
     tc_fence_before();
     __syncwarp();

@@ -25,6 +25,7 @@ struct ScanParams {
   const float* inv_norm_q;  // [B] 1/||bf16(q)||
   unsigned int* hist;       // [B][kHistBins] scores of all appended rows (zeroed per launch)
   int* maxbin;              // [B] highest occupied histogram bin (zeroed per launch)
+  unsigned int* gthr;       // [B] best published threshold per query, f32_ordered (0 = none; zeroed per launch)
   int* progress;            // [R][QB] tiles issued by each CTA's producer (zeroed per launch)
   unsigned long long* cand; // [QB][R][kBlockM][kListCap] packed keys
   int* cand_cnt;            // [QB][R][kBlockM]

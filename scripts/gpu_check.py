@@ -101,12 +101,12 @@ def stage_time(n=1_000_000, d=768, b=256, k=32, iters=5, tag="time"):
     ix.close()
 
 
-def stage_sweep():
-    """scan time vs N at B=1024 (fixed per-launch cost of the scan kernel)."""
+def stage_sweep(b=1024):
+    """scan time vs N at fixed B (fixed per-launch cost of the scan kernel)."""
     import numpy as np
     import torch
     from runbookai_b200 import Index, synth
-    d, b, k = 768, 1024, 32
+    d, k = 768, 32
     q = synth.random_queries(b, d, 8).astype(np.float32)
     g = torch.Generator(device="cuda").manual_seed(7)
     ix = Index(d, capacity_hint=4_000_000)
@@ -139,6 +139,8 @@ STAGES = {
     "time2": lambda: stage_time(n=2_000_000, b=1024, tag="time2"),
     "time3": lambda: stage_time(n=1_000_000, b=1, k=10, tag="time3"),
     "sweep": lambda: stage_sweep(),
+    "sweep256": lambda: stage_sweep(256),
+    "sweep1": lambda: stage_sweep(1),
 }
 
 if __name__ == "__main__":
