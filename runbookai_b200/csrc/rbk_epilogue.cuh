@@ -14,6 +14,9 @@
 #include "rbk_internal.h"
 #include "rbk_ptx.cuh"
 
+#ifdef RBK_EPI_PROFILE
+#include <cstdio>
+#endif
 namespace rbk {
 
 struct FilterState {
@@ -25,6 +28,7 @@ struct FilterState {
   int cnt;         // entries in the list
   bool valid;
   int probe;       // timing experiments only (ScanParams::perf_probe)
+  bool nohist;     // appends are not counted in the histogram (second pass over a seeded tile)
   unsigned long long* list;
   unsigned int* hist_q;  // [kHistBins]
   int* maxbin_q;
@@ -50,6 +54,7 @@ __device__ __forceinline__ void filter_init(FilterState& s, bool valid, float th
   s.tb = (s.valid && thr_init > -INFINITY) ? score_bin(thr_init * inv_q) : -1;
   s.mb_cache = -1;
   s.probe = 0;
+  s.nohist = false;
   s.cnt = 0;
   s.list = list;
   s.hist_q = hist_q;
@@ -59,10 +64,10 @@ __device__ __forceinline__ void filter_init(FilterState& s, bool valid, float th
 // Raise thr from the global histogram (source 3).  Per-thread, no warp collectives.
 // Bins are fetched 16 at a time (four independent 16-byte L2 loads in flight): a dependent chain
 // of single loads cost ~0.7 us per 4 bins and made this function 23 % of the epilogue's time.
-static __device__ __noinline__ void filter_refresh(FilterState& s, int kprime) {
-  if (!s.valid || s.probe == 3) return;
+static __device__ __noinline__ bool filter_refresh(FilterState& s, int kprime) {
+  if (!s.valid || s.probe == 3) return false;
   const int mb = __ldcg(s.maxbin_q);
-  if (mb <= s.tb) return;
+  if (mb <= s.tb) return false;
   const uint4* h4 = reinterpret_cast<const uint4*>(s.hist_q);
   const int g_lo = (s.tb + 1) >> 2;   // lowest group that may hold a bin > tb
   unsigned cum = 0;
@@ -82,12 +87,13 @@ static __device__ __noinline__ void filter_refresh(FilterState& s, int kprime) {
           if (cum >= static_cast<unsigned>(kprime)) {
             s.tb = b;
             s.thr = fmaxf(s.thr, bin_edge_raw(b, s.qn));
-            return;
+            return true;
           }
         }
       }
     }
   }
+  return false;
 }
 
 // When to refresh: every tile while the threshold is still moving fast, then ever more rarely
@@ -114,16 +120,49 @@ __device__ __forceinline__ void adopt_threshold(FilterState& s, unsigned int ord
   s.thr = fmaxf(s.thr, f32_from_ordered(ordered));   // 0 (nothing published) decodes to NaN, which fmaxf drops
 }
 
-__device__ __forceinline__ void filter_append(FilterState& s, float t, uint32_t row) {
-  s.list[s.cnt] = pack_key(t, row);
-  ++s.cnt;
-  if (s.probe == 3) return;   // probe: no histogram
+// Count one row of raw score t in the query's global histogram.  Every row must be counted AT MOST once:
+// the counts are lower bounds on "rows of the corpus with a score in this bin", which is what makes a
+// threshold read off the histogram safe.
+__device__ __forceinline__ void hist_add(FilterState& s, float t) {
   const int b = score_bin(t * s.inv_q);
   atomicAdd(s.hist_q + b, 1u);
   if (b > s.mb_cache) {
     atomicMax(s.maxbin_q, b);
     s.mb_cache = b;
   }
+}
+
+__device__ __forceinline__ void filter_append(FilterState& s, float t, uint32_t row) {
+  s.list[s.cnt] = pack_key(t, row);
+  ++s.cnt;
+  if (s.nohist || s.probe == 3) return;
+  hist_add(s, t);
+}
+
+// Seeding pass over a unit's FIRST tile.  With no threshold yet, the plain filter appends (and counts) every
+// row it sees until the histogram holds k' rows: measured on B200, those few hundred appends per thread cost
+// 50-100 k cycles per unit (scattered 8-byte stores plus ~5 k atomics per query landing on the same three or
+// four histogram lines from every SM at once) - 80 us of fixed cost per search.  Instead the first tile is
+// read twice: this pass only counts the two best group maxima of every 32-column chunk (two distinct rows,
+// 16 per unit and tile, which is where the query's best rows so far are with overwhelming probability), all
+// units' seeds then give the threshold, and the regular pass over the same accumulators appends the handful
+// of rows above it - without counting them again.
+__device__ __forceinline__ void seed_chunk(FilterState& s, const uint32_t (&v)[32], const float* invc32) {
+  const float4* ic4 = reinterpret_cast<const float4*>(invc32);
+  float m1 = -INFINITY, m2 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 w = ic4[j];
+    const float a0 = __uint_as_float(v[4 * j + 0]) * w.x;
+    const float a1 = __uint_as_float(v[4 * j + 1]) * w.y;
+    const float a2 = __uint_as_float(v[4 * j + 2]) * w.z;
+    const float a3 = __uint_as_float(v[4 * j + 3]) * w.w;
+    const float x = fmaxf(fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)), -INFINITY);   // a group of dead rows: NaN -> -inf
+    m2 = fmaxf(m2, fminf(m1, x));
+    m1 = fmaxf(m1, x);
+  }
+  if (m1 > s.thr) hist_add(s, m1);
+  if (m2 > s.thr) hist_add(s, m2);
 }
 
 // 32 accumulator columns of this thread's query; invc32 = the 32 matching 1/||c|| (smem).
@@ -271,6 +310,15 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
               p.cand + (static_cast<size_t>(qb * p.R + r) * kBlockQ + qin) * static_cast<size_t>(kListCap),
               p.hist + static_cast<size_t>(q_valid ? q : 0) * kHistBins, p.maxbin + (q_valid ? q : 0));
   fs.probe = p.perf_probe;
+#ifdef RBK_EPI_PROFILE   // cycle breakdown of one epilogue thread per CTA (development builds only)
+  long long c_wait = 0, c_chunk = 0, c_compact = 0, c_pub = 0, c_bar = 0, c_seed = 0;
+  long long c_tile[4] = {0, 0, 0, 0}, c_sub[4] = {0, 0, 0, 0};
+  int n_tile[4] = {0, 0, 0, 0};
+  const long long c_begin = clock64();
+#define RBK_PROF(var, ...) { const long long t_ = clock64(); __VA_ARGS__; var += clock64() - t_; }
+#else
+#define RBK_PROF(var, ...) { __VA_ARGS__; }
+#endif
   int as = 0;
   uint32_t aph = 0;
   // the next tile's 1/||c|| travels in registers while this tile is processed (hides its L2/HBM latency)
@@ -293,9 +341,9 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
     }
     adopt_threshold(fs, ngt);
     ngt = __ldcg(gthr_q);
-    named_bar_sync(1, kEpi);
-    if (publish_due(it) && r == it % p.R) publish_threshold(fs, gthr_q, p.kprime);   // overlaps this tile's MMAs
-    mbar_wait(smem_u32(&tmem_full[as]), aph);
+    RBK_PROF(c_bar, named_bar_sync(1, kEpi));
+    RBK_PROF(c_pub, if (publish_due(it) && r == it % p.R) publish_threshold(fs, gthr_q, p.kprime));   // overlaps this tile's MMAs
+    RBK_PROF(c_wait, mbar_wait(smem_u32(&tmem_full[as]), aph));
     tc_fence_after();
     // Two chunks in flight: the TMEM load of the next 32 columns is issued before the current 32 are
     // filtered, so its latency overlaps the arithmetic (one epilogue warp per SM sub-partition is
@@ -317,21 +365,58 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
       }
     };
     uint32_t va[32], vb[32];
+    if (it == 0 && p.perf_probe == 0) {
+      // seeding pass (see seed_chunk): count the best rows of this tile, then take the threshold they give
+#ifdef RBK_EPI_PROFILE
+      const long long t_seed = clock64();
+#endif
+      tmem_ld_32x32b_x32(tcol, va);
+#pragma unroll 1
+      for (int c2 = 0; c2 < kBlockN / 64; ++c2) {
+        tmem_wait_ld_dep(va);
+        tmem_ld_32x32b_x32(tcol + static_cast<uint32_t>((2 * c2 + 1) * 32), vb);
+        seed_chunk(fs, va, invc + (2 * c2) * 32);
+        tmem_wait_ld_dep(vb);
+        if (c2 + 1 < kBlockN / 64) tmem_ld_32x32b_x32(tcol + static_cast<uint32_t>((2 * c2 + 2) * 32), va);
+        seed_chunk(fs, vb, invc + (2 * c2 + 1) * 32);
+      }
+      // the other units' seeds land within a microsecond or so of ours: a few short retries when the
+      // histogram cannot hold k' rows yet but soon will (R units x 16 seeds)
+      const int tries = (p.R * 16 >= 2 * p.kprime) ? 6 : 1;
+      for (int t = 0; t < tries; ++t) {
+        const bool found = filter_refresh(fs, p.kprime);
+        if (__all_sync(0xFFFFFFFFu, found || !fs.valid)) break;
+        if (t + 1 < tries) __nanosleep(400);
+      }
+      if (fs.valid && fs.thr > -INFINITY) atomicMax(gthr_q, f32_ordered(fs.thr));
+      fs.nohist = true;
+#ifdef RBK_EPI_PROFILE
+      c_seed += clock64() - t_seed;
+#endif
+    }
     tmem_ld_32x32b_x32(tcol, va);
 #pragma unroll 1
     for (int c2 = 0; c2 < kBlockN / 64; ++c2) {
-      tmem_wait_ld_dep(va);
-      tmem_ld_32x32b_x32(tcol + static_cast<uint32_t>((2 * c2 + 1) * 32), vb);
-      process(va, 2 * c2);
-      tmem_wait_ld_dep(vb);
-      if (c2 + 1 < kBlockN / 64) tmem_ld_32x32b_x32(tcol + static_cast<uint32_t>((2 * c2 + 2) * 32), va);
-      process(vb, 2 * c2 + 1);
-      filter_compact_if_needed(fs, p.kprime, lane, 64);
-      if (it == 0 && t1 - t0 > 2) {   // start-up: converge within the first tile (pointless for a tile or two)
-        if (r == c2 % p.R) publish_threshold(fs, gthr_q, p.kprime);
-        else adopt_threshold(fs, __ldcg(gthr_q));
-      }
+#ifdef RBK_EPI_PROFILE
+      const long long c_before = c_chunk;
+#endif
+      RBK_PROF(c_chunk,
+        tmem_wait_ld_dep(va);
+        tmem_ld_32x32b_x32(tcol + static_cast<uint32_t>((2 * c2 + 1) * 32), vb);
+        process(va, 2 * c2);
+        tmem_wait_ld_dep(vb);
+        if (c2 + 1 < kBlockN / 64) tmem_ld_32x32b_x32(tcol + static_cast<uint32_t>((2 * c2 + 2) * 32), va);
+        process(vb, 2 * c2 + 1));
+#ifdef RBK_EPI_PROFILE
+      c_tile[it < 3 ? it : 3] += c_chunk - c_before;
+      if (it == 0) c_sub[c2] = c_chunk - c_before;
+      n_tile[it < 3 ? it : 3] = fs.cnt;
+#endif
+      RBK_PROF(c_compact, filter_compact_if_needed(fs, p.kprime, lane, 64));
+      // seeding found nothing (too few units, or their seeds were late): keep looking while the tile is filtered
+      if (it == 0 && fs.valid && fs.thr == -INFINITY) adopt_threshold(fs, __ldcg(gthr_q));
     }
+    fs.nohist = false;
     tc_fence_before();
     __syncwarp();
     if (lane == 0) {
@@ -342,6 +427,16 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
     if (as == 0) aph ^= 1u;
   }
   p.cand_cnt[(qb * p.R + r) * kBlockQ + qin] = fs.cnt;
+#ifdef RBK_EPI_PROFILE
+  if (et == 0 && (r == 0 || r == 1 || r == p.R - 1) && qb == 0 && rank == 0)
+    printf("[epi r=%d tiles=%d] total %lld  bar %lld  publish %lld  wait_full %lld  chunks %lld  compact %lld  seed %lld  cnt %d\n", r,
+           t1 - t0, clock64() - c_begin, c_bar, c_pub, c_wait, c_chunk, c_compact, c_seed, fs.cnt);
+  if (et == 0 && (r == 0 || r == 1 || r == p.R - 1) && qb == 0 && rank == 0)
+    printf("[epi r=%d] tile0 %lld (%lld %lld %lld %lld) cnt %d | tile1 %lld cnt %d | tile2 %lld cnt %d | rest %lld cnt %d\n", r,
+           c_tile[0], c_sub[0], c_sub[1], c_sub[2], c_sub[3], n_tile[0], c_tile[1], n_tile[1], c_tile[2], n_tile[2],
+           c_tile[3], n_tile[3]);
+#endif
+#undef RBK_PROF
 }
 
 // Bounded-lag lockstep of the QB producers that stream the same corpus range: nobody runs
