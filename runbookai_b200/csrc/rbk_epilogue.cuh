@@ -120,6 +120,19 @@ __device__ __forceinline__ void adopt_threshold(FilterState& s, unsigned int ord
   s.thr = fmaxf(s.thr, f32_from_ordered(ordered));   // 0 (nothing published) decodes to NaN, which fmaxf drops
 }
 
+// 1/||c|| of a chunk's rows: from shared memory (staged per tile) or, kGlobal, straight from the corpus-norm
+// array through L1 (every lane reads the same address: one broadcast transaction).
+template <bool kGlobal>
+__device__ __forceinline__ float4 norm4(const float4* p) {
+  if constexpr (kGlobal) return __ldg(p);
+  else return *p;
+}
+template <bool kGlobal>
+__device__ __forceinline__ float norm1(const float* p) {
+  if constexpr (kGlobal) return __ldg(p);
+  else return *p;
+}
+
 // Count one row of raw score t in the query's global histogram.  Every row must be counted AT MOST once:
 // the counts are lower bounds on "rows of the corpus with a score in this bin", which is what makes a
 // threshold read off the histogram safe.
@@ -147,12 +160,13 @@ __device__ __forceinline__ void filter_append(FilterState& s, float t, uint32_t 
 // 16 per unit and tile, which is where the query's best rows so far are with overwhelming probability), all
 // units' seeds then give the threshold, and the regular pass over the same accumulators appends the handful
 // of rows above it - without counting them again.
+template <bool kGlobal = false>
 __device__ __forceinline__ void seed_chunk(FilterState& s, const uint32_t (&v)[32], const float* invc32) {
   const float4* ic4 = reinterpret_cast<const float4*>(invc32);
   float m1 = -INFINITY, m2 = -INFINITY;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float4 w = ic4[j];
+    const float4 w = norm4<kGlobal>(ic4 + j);
     const float a0 = __uint_as_float(v[4 * j + 0]) * w.x;
     const float a1 = __uint_as_float(v[4 * j + 1]) * w.y;
     const float a2 = __uint_as_float(v[4 * j + 2]) * w.z;
@@ -165,7 +179,8 @@ __device__ __forceinline__ void seed_chunk(FilterState& s, const uint32_t (&v)[3
   if (m2 > s.thr) hist_add(s, m2);
 }
 
-// 32 accumulator columns of this thread's query; invc32 = the 32 matching 1/||c|| (smem).
+// 32 accumulator columns of this thread's query; invc32 = the 32 matching 1/||c||.
+template <bool kGlobal = false>
 __device__ __forceinline__ void filter_chunk(FilterState& s, const uint32_t (&v)[32], const float* invc32,
                                              uint32_t row_base) {
   const float4* ic4 = reinterpret_cast<const float4*>(invc32);
@@ -173,7 +188,7 @@ __device__ __forceinline__ void filter_chunk(FilterState& s, const uint32_t (&v)
   float m = -INFINITY;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float4 w = ic4[j];
+    const float4 w = norm4<kGlobal>(ic4 + j);
     const float a0 = __uint_as_float(v[4 * j + 0]) * w.x;
     const float a1 = __uint_as_float(v[4 * j + 1]) * w.y;
     const float a2 = __uint_as_float(v[4 * j + 2]) * w.z;
@@ -194,7 +209,7 @@ __device__ __forceinline__ void filter_chunk(FilterState& s, const uint32_t (&v)
       if (g[j] > s.thr) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float t = __uint_as_float(v[4 * j + e]) * invc32[4 * j + e];
+          const float t = __uint_as_float(v[4 * j + e]) * norm1<kGlobal>(invc32 + 4 * j + e);
           if (t > s.thr) filter_append(s, t, row_base + 4 * j + e);
         }
       }
@@ -322,16 +337,33 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
   int as = 0;
   uint32_t aph = 0;
   // the next tile's 1/||c|| travels in registers while this tile is processed (hides its L2/HBM latency)
+  // 1/||c|| of a tile's 256 rows are staged in shared memory, one 128-thread barrier per tile (the four
+  // epilogue warps wait for the slowest of the previous tile there).  -DRBK_NORMS_L1 builds the alternative
+  // that was tried to get rid of that barrier - every warp reads the norms straight from the array through
+  // L1 with uniform 16-byte loads, next tile prefetched - and measured 15-25 % SLOWER on B200 (cfg2 scan
+  // 0.34 -> 0.42 ms, B=1024 x 4M rows 4.87 -> 5.43 ms): the L1 round trip of 8 loads per chunk costs more
+  // than the barrier wait it removes.
+#ifndef RBK_NORMS_L1
+  constexpr bool kGN = false;
   float nx0 = 0.f, nx1 = 0.f;
+#else
+  constexpr bool kGN = true;
+  (void)invc_stage;
+#endif
   unsigned int* gthr_q = p.gthr + (q_valid ? q : 0);
-  unsigned int ngt = 0u;   // published threshold, fetched one tile ahead like the norms
+  unsigned int ngt = 0u;   // published threshold, fetched one tile ahead
   if (t0 < t1) {
+#ifndef RBK_NORMS_L1
     nx0 = __ldg(p.inv_norm_c + t0 * kBlockN + et);
     nx1 = __ldg(p.inv_norm_c + t0 * kBlockN + kEpi + et);
+#else
+    if (lane < kBlockN / 32) prefetch_l1(p.inv_norm_c + static_cast<size_t>(t0) * kBlockN + lane * 32);
+#endif
   }
   for (int tile = t0; tile < t1; ++tile) {
     const int row0 = tile * kBlockN;
     const int it = tile - t0;
+#ifndef RBK_NORMS_L1
     float* invc = invc_stage[as];
     invc[et] = nx0;
     invc[kEpi + et] = nx1;
@@ -339,9 +371,16 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
       nx0 = __ldg(p.inv_norm_c + (tile + 1) * kBlockN + et);
       nx1 = __ldg(p.inv_norm_c + (tile + 1) * kBlockN + kEpi + et);
     }
+#else
+    const float* invc = p.inv_norm_c + static_cast<size_t>(row0);
+    if (tile + 1 < t1 && lane < kBlockN / 32)
+      prefetch_l1(p.inv_norm_c + static_cast<size_t>(tile + 1) * kBlockN + lane * 32);
+#endif
     adopt_threshold(fs, ngt);
     ngt = __ldcg(gthr_q);
+#ifndef RBK_NORMS_L1
     RBK_PROF(c_bar, named_bar_sync(1, kEpi));
+#endif
     RBK_PROF(c_pub, if (publish_due(it) && r == it % p.R) publish_threshold(fs, gthr_q, p.kprime));   // overlaps this tile's MMAs
     RBK_PROF(c_wait, mbar_wait(smem_u32(&tmem_full[as]), aph));
     tc_fence_after();
@@ -354,7 +393,7 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
         if (v[0] == 0x7FC12345u) fs.cnt = 1;
         return;
       }
-      filter_chunk(fs, v, invc + chunk * 32, static_cast<uint32_t>(row0 + chunk * 32));
+      filter_chunk<kGN>(fs, v, invc + chunk * 32, static_cast<uint32_t>(row0 + chunk * 32));
       if (p.dbg_scores != nullptr && q_valid) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -375,10 +414,10 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
       for (int c2 = 0; c2 < kBlockN / 64; ++c2) {
         tmem_wait_ld_dep(va);
         tmem_ld_32x32b_x32(tcol + static_cast<uint32_t>((2 * c2 + 1) * 32), vb);
-        seed_chunk(fs, va, invc + (2 * c2) * 32);
+        seed_chunk<kGN>(fs, va, invc + (2 * c2) * 32);
         tmem_wait_ld_dep(vb);
         if (c2 + 1 < kBlockN / 64) tmem_ld_32x32b_x32(tcol + static_cast<uint32_t>((2 * c2 + 2) * 32), va);
-        seed_chunk(fs, vb, invc + (2 * c2 + 1) * 32);
+        seed_chunk<kGN>(fs, vb, invc + (2 * c2 + 1) * 32);
       }
       // the other units' seeds land within a microsecond or so of ours: a few short retries when the
       // histogram cannot hold k' rows yet but soon will (R units x 16 seeds)

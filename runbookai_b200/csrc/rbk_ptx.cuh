@@ -49,6 +49,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 // ---------------------------------------------------------------- TMA
+// Pull one 128-byte line into L1 (no register result, no scoreboard wait).
+__device__ __forceinline__ void prefetch_l1(const void* gptr) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<uint64_t>(gptr)) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
