@@ -156,6 +156,7 @@ struct rbk_index {
   CUtensorMap tmap_c, tmap_c_half, tmap_c_half32, tmap_c_pf, tmap_c_r32;
   int perf_probe = 0;
   int max_lead_tiles = kMaxLeadTiles;
+  int epi_halves = 0;        // 0 = default (2); RBK_KNN_HALVES=1|2 forces
   int hybrid_res_kb = -1, hybrid_slots = 8;   // -1: hybrid pair kernel off
   bool use_ts = false;  // pair kernel with queries in TMEM (dim <= 768): correct but not yet faster
   bool force_1cta = false, force_streamed = true;   // query-resident pair kernel: measured slower
@@ -318,8 +319,8 @@ rbk_status ensure_query_scratch(rbk_index* ix, int B, int elem) {
   CK(ix->q_inv_norm.ensure(B));
   CK(ix->thr_init.ensure(B));
   CK(ix->flags.ensure(B));
-  CK(ix->cand.ensure(static_cast<size_t>(ix->sm_count) * kBlockM * kListCap));
-  CK(ix->cand_cnt.ensure(static_cast<size_t>(ix->sm_count) * kBlockM));
+  CK(ix->cand.ensure(static_cast<size_t>(ix->sm_count) * kBlockM * kListCap * kMaxHalves));
+  CK(ix->cand_cnt.ensure(static_cast<size_t>(ix->sm_count) * kBlockM * kMaxHalves));
   // hist [kMaxSubBatch][kHistBins] | maxbin [kMaxSubBatch] | gthr [kMaxSubBatch] | progress [sm_count + 8]:
   // one buffer, one memset
   CK(ix->hist.ensure(static_cast<size_t>(kMaxSubBatch) * kHistBins + 2 * kMaxSubBatch + ix->sm_count + 8));
@@ -403,13 +404,21 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
     sp.perf_probe = ix->perf_probe;
     sp.max_lead_tiles = ix->max_lead_tiles;
     const bool ts = pairs && ix->use_ts && scan3_fits(ix->dpad);
+    // lists per (unit, query): the default pair kernel splits every tile between two sets of epilogue warps
+    // Eight epilogue warps (two lists per unit and query): measured in one box against four, +7-10 % at
+    // B=256 up to 1M rows and +10-17 % at B=1024 up to 0.5M rows (where the filter is busy: thresholds still
+    // rising, appends frequent), +-1 % on long scans (cfg3).  RBK_KNN_HALVES=1 forces the narrow epilogue.
+    int halves = 1;
+    if (pairs && !ts && ix->hybrid_res_kb < 0) {
+      halves = ix->epi_halves > 0 ? std::min(ix->epi_halves, kMaxHalves) : kMaxHalves;
+    }
     if (pairs && !ts && ix->hybrid_res_kb >= 0)
       CK(launch_scan2h(tmap_q, ix->tmap_c_half, sp, ix->hybrid_res_kb, ix->hybrid_slots, ix->stream));
     else if (ts)
       CK(launch_scan3(ix->tmap_c_r32, sp, ix->q_bf16.p + static_cast<size_t>(q0) * ix->dpad, ix->stream));
     else if (pairs)
       CK(launch_scan2(tmap_q, (resident && scan2_resident_k() == 32) ? ix->tmap_c_half32 : ix->tmap_c_half,
-                      ix->tmap_c_pf, sp, resident, ix->stream, &ix->stats.last_ring_stages));
+                      ix->tmap_c_pf, sp, resident, halves, ix->stream, &ix->stats.last_ring_stages));
     else CK(launch_scan(tmap_q, ix->tmap_c, sp, ix->stream));
     CK(cudaEventRecord(get_event(ix, (*ev_cursor)++), ix->stream));
     ix->stats.scan_launches++;
@@ -419,7 +428,7 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
       fp.cand = ix->cand.p;
       fp.cand_cnt = ix->cand_cnt.p;
       fp.QB = QB;
-      fp.R = R;
+      fp.R = R * halves;   // finalize sees every list as a unit of its own
       fp.kprime = kprime;
       fp.k_fetch = k_fetch;
       fp.B = Bs;
@@ -610,6 +619,7 @@ rbk_status rbk_index_create_ex(int32_t dim, int32_t device, int64_t capacity_hin
   if (const char* m = getenv("RBK_KNN_RESIDENT")) ix->force_streamed = atoi(m) == 0;   // experiments only
   if (const char* m = getenv("RBK_KNN_TS")) ix->use_ts = atoi(m) != 0;
   if (const char* m = getenv("RBK_KNN_MAX_LEAD")) ix->max_lead_tiles = std::max(1, atoi(m));
+  if (const char* m = getenv("RBK_KNN_HALVES")) ix->epi_halves = std::max(0, atoi(m));
   if (const char* m = getenv("RBK_KNN_PERF_PROBE")) ix->perf_probe = atoi(m);   // breaks results; timing only
   if (const char* m = getenv("RBK_KNN_HYBRID_KB")) ix->hybrid_res_kb = atoi(m);
   if (const char* m = getenv("RBK_KNN_HYBRID_SLOTS")) ix->hybrid_slots = atoi(m);

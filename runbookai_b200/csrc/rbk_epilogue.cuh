@@ -304,25 +304,35 @@ __device__ __forceinline__ void filter_compact_if_needed(FilterState& s, int kpr
 }
 
 
-// The whole epilogue role (4 warps, 128 threads, thread <-> query) shared by the scan
-// kernels.  kPair: CTA-pair kernels (256-query blocks, remote arrive on the leader's
-// tmem_empty barrier).  invc: per-accumulator-stage staging of the tile's 1/||c||.
-template <bool kPair>
+// The whole epilogue role (thread <-> query) shared by the scan kernels.  kPair: CTA-pair kernels (256-query
+// blocks, remote arrive on the leader's tmem_empty barrier).  invc: per-accumulator-stage staging of the
+// tile's 1/||c||.
+// kHalves = 1: 4 warps, each thread filters all 256 columns of a tile for its query.
+// kHalves = 2: 8 warps (warps 2-5 take columns 0-127, warps 6-9 columns 128-255; a warp may only read the
+// TMEM lane quadrant warp%4, which both sets cover), every thread with its own candidate list - to the
+// finalize kernel a unit simply looks like two.  One epilogue warp per SM sub-partition is latency-bound
+// (~0.15 IPC: dependent TMEM-load / multiply / max chains and divergent append blocks with nothing to
+// overlap them); two per sub-partition hide each other's latencies and halve the per-tile work of each.
+template <bool kPair, int kHalves = 1>
 __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_stage)[kBlockN],
                                              unsigned long long* tmem_full, unsigned long long* tmem_empty,
                                              uint32_t tmem_base, int qb, int r, uint32_t rank, int t0, int t1,
                                              int warp, int lane) {
-  constexpr int kEpi = 128;
+  constexpr int kEpi = 128 * kHalves;
   constexpr int kBlockQ = kPair ? 2 * kBlockM : kBlockM;
+  constexpr int kCols = kBlockN / kHalves;          // columns of a tile this thread filters
+  const int half = kHalves == 2 ? ((warp - 2) >> 2) : 0;
+  const int col0 = half * kCols;
   const int quad = warp & 3;            // TMEM lane quadrant this warp may read
   const int qrow = quad * 32 + lane;    // TMEM lane
   const int qin = (kPair ? static_cast<int>(rank) * kBlockM : 0) + qrow;   // row inside the query block
   const int q = qb * kBlockQ + qin;
   const bool q_valid = q < p.B;
-  const int et = threadIdx.x - 64;      // 0..127
+  const int et = threadIdx.x - 64;      // 0..kEpi-1
+  const size_t list_id = static_cast<size_t>((qb * p.R + r) * kHalves + half) * kBlockQ + qin;
   FilterState fs;
   filter_init(fs, q_valid, q_valid ? p.thr_init[q] : INFINITY, q_valid ? p.inv_norm_q[q] : 0.f,
-              p.cand + (static_cast<size_t>(qb * p.R + r) * kBlockQ + qin) * static_cast<size_t>(kListCap),
+              p.cand + list_id * static_cast<size_t>(kListCap),
               p.hist + static_cast<size_t>(q_valid ? q : 0) * kHistBins, p.maxbin + (q_valid ? q : 0));
   fs.probe = p.perf_probe;
 #ifdef RBK_EPI_PROFILE   // cycle breakdown of one epilogue thread per CTA (development builds only)
@@ -355,7 +365,7 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
   if (t0 < t1) {
 #ifndef RBK_NORMS_L1
     nx0 = __ldg(p.inv_norm_c + t0 * kBlockN + et);
-    nx1 = __ldg(p.inv_norm_c + t0 * kBlockN + kEpi + et);
+    if (kHalves == 1) nx1 = __ldg(p.inv_norm_c + t0 * kBlockN + kEpi + et);
 #else
     if (lane < kBlockN / 32) prefetch_l1(p.inv_norm_c + static_cast<size_t>(t0) * kBlockN + lane * 32);
 #endif
@@ -366,10 +376,10 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
 #ifndef RBK_NORMS_L1
     float* invc = invc_stage[as];
     invc[et] = nx0;
-    invc[kEpi + et] = nx1;
+    if (kHalves == 1) invc[kEpi + et] = nx1;
     if (tile + 1 < t1) {
       nx0 = __ldg(p.inv_norm_c + (tile + 1) * kBlockN + et);
-      nx1 = __ldg(p.inv_norm_c + (tile + 1) * kBlockN + kEpi + et);
+      if (kHalves == 1) nx1 = __ldg(p.inv_norm_c + (tile + 1) * kBlockN + kEpi + et);
     }
 #else
     const float* invc = p.inv_norm_c + static_cast<size_t>(row0);
@@ -381,25 +391,27 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
 #ifndef RBK_NORMS_L1
     RBK_PROF(c_bar, named_bar_sync(1, kEpi));
 #endif
-    RBK_PROF(c_pub, if (publish_due(it) && r == it % p.R) publish_threshold(fs, gthr_q, p.kprime));   // overlaps this tile's MMAs
+    RBK_PROF(c_pub, if (publish_due(it) && r == it % p.R && half == 0) publish_threshold(fs, gthr_q, p.kprime));   // overlaps this tile's MMAs
     RBK_PROF(c_wait, mbar_wait(smem_u32(&tmem_full[as]), aph));
     tc_fence_after();
     // Two chunks in flight: the TMEM load of the next 32 columns is issued before the current 32 are
     // filtered, so its latency overlaps the arithmetic (one epilogue warp per SM sub-partition is
     // latency-bound: ~1000 cycles per chunk measured with load -> wait -> compute in sequence).
-    const uint32_t tcol = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * kBlockN);
+    const uint32_t tcol =
+        tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * kBlockN + col0);
     auto process = [&](uint32_t (&v)[32], int chunk) {
       if (p.perf_probe == 1) {   // timing probe: keep the TMEM traffic, drop the arithmetic
         if (v[0] == 0x7FC12345u) fs.cnt = 1;
         return;
       }
-      filter_chunk<kGN>(fs, v, invc + chunk * 32, static_cast<uint32_t>(row0 + chunk * 32));
+      filter_chunk<kGN>(fs, v, invc + col0 + chunk * 32, static_cast<uint32_t>(row0 + col0 + chunk * 32));
       if (p.dbg_scores != nullptr && q_valid) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int row = row0 + chunk * 32 + j;
+          const int row = row0 + col0 + chunk * 32 + j;
           if (row < p.n_rows)
-            p.dbg_scores[static_cast<size_t>(q) * p.n_rows + row] = __uint_as_float(v[j]) * invc[chunk * 32 + j];
+            p.dbg_scores[static_cast<size_t>(q) * p.n_rows + row] =
+                __uint_as_float(v[j]) * invc[col0 + chunk * 32 + j];
         }
       }
     };
@@ -411,13 +423,13 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
 #endif
       tmem_ld_32x32b_x32(tcol, va);
 #pragma unroll 1
-      for (int c2 = 0; c2 < kBlockN / 64; ++c2) {
+      for (int c2 = 0; c2 < kCols / 64; ++c2) {
         tmem_wait_ld_dep(va);
         tmem_ld_32x32b_x32(tcol + static_cast<uint32_t>((2 * c2 + 1) * 32), vb);
-        seed_chunk<kGN>(fs, va, invc + (2 * c2) * 32);
+        seed_chunk<kGN>(fs, va, invc + col0 + (2 * c2) * 32);
         tmem_wait_ld_dep(vb);
-        if (c2 + 1 < kBlockN / 64) tmem_ld_32x32b_x32(tcol + static_cast<uint32_t>((2 * c2 + 2) * 32), va);
-        seed_chunk<kGN>(fs, vb, invc + (2 * c2 + 1) * 32);
+        if (c2 + 1 < kCols / 64) tmem_ld_32x32b_x32(tcol + static_cast<uint32_t>((2 * c2 + 2) * 32), va);
+        seed_chunk<kGN>(fs, vb, invc + col0 + (2 * c2 + 1) * 32);
       }
       // the other units' seeds land within a microsecond or so of ours: a few short retries when the
       // histogram cannot hold k' rows yet but soon will (R units x 16 seeds)
@@ -435,7 +447,7 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
     }
     tmem_ld_32x32b_x32(tcol, va);
 #pragma unroll 1
-    for (int c2 = 0; c2 < kBlockN / 64; ++c2) {
+    for (int c2 = 0; c2 < kCols / 64; ++c2) {
 #ifdef RBK_EPI_PROFILE
       const long long c_before = c_chunk;
 #endif
@@ -444,7 +456,7 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
         tmem_ld_32x32b_x32(tcol + static_cast<uint32_t>((2 * c2 + 1) * 32), vb);
         process(va, 2 * c2);
         tmem_wait_ld_dep(vb);
-        if (c2 + 1 < kBlockN / 64) tmem_ld_32x32b_x32(tcol + static_cast<uint32_t>((2 * c2 + 2) * 32), va);
+        if (c2 + 1 < kCols / 64) tmem_ld_32x32b_x32(tcol + static_cast<uint32_t>((2 * c2 + 2) * 32), va);
         process(vb, 2 * c2 + 1));
 #ifdef RBK_EPI_PROFILE
       c_tile[it < 3 ? it : 3] += c_chunk - c_before;
@@ -465,7 +477,7 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
     as ^= 1;
     if (as == 0) aph ^= 1u;
   }
-  p.cand_cnt[(qb * p.R + r) * kBlockQ + qin] = fs.cnt;
+  p.cand_cnt[list_id] = fs.cnt;
 #ifdef RBK_EPI_PROFILE
   if (et == 0 && (r == 0 || r == 1 || r == p.R - 1) && qb == 0 && rank == 0)
     printf("[epi r=%d tiles=%d] total %lld  bar %lld  publish %lld  wait_full %lld  chunks %lld  compact %lld  seed %lld  cnt %d\n", r,

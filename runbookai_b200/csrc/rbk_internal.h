@@ -14,6 +14,8 @@ constexpr int kStages = 4;        // smem ring depth
 constexpr int kListCap = 256;     // entries per (CTA, query) candidate list
 constexpr int kMaxKPrime = 128;   // candidates kept per query (k_fetch + margin)
 constexpr int kScanThreads = 192; // warp0 TMA, warp1 MMA/TMEM, warps2-5 epilogue
+// the CTA-pair kernel (rbk_scan2.cu) can run 8 epilogue warps: two column halves per tile, two lists per (unit, query)
+constexpr int kMaxHalves = 2;
 constexpr int kMaxSubBatch = 1024;  // queries per scan launch (8 query blocks)
 constexpr int kMaxLeadTiles = 4;    // lockstep: max tiles a CTA may lead the slowest peer of its range (A/B on cfg3
                                     // under the power cap: 8 -> 74.2 k, 4 -> 76.4 k, 2 -> 77.4 k q/s; short kernels: 8 best by 2 %)
@@ -50,7 +52,8 @@ size_t scan_smem_bytes();
 // 64 columns / SWIZZLE_128B for the streamed kernel, 32 columns / SWIZZLE_64B for the query-resident one.
 // tmap_pf: un-swizzled 128-row x 256-col boxes, used only for L2 prefetch.
 cudaError_t launch_scan2(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const CUtensorMap& tmap_pf,
-                         const ScanParams& p, bool resident, cudaStream_t stream, int* ring_stages_out = nullptr);
+                         const ScanParams& p, bool resident, int halves, cudaStream_t stream,
+                         int* ring_stages_out = nullptr);
 // CTA-pair kernel with the query operand in TMEM (rbk_scan3.cu): dpad <= 768.  tmap_c: 32-row x 64-col boxes.
 cudaError_t launch_scan3(const CUtensorMap& tmap_c, const ScanParams& p, const uint16_t* q_bf16, cudaStream_t stream);
 bool scan3_fits(int dpad);

@@ -70,8 +70,8 @@ __device__ __forceinline__ uint64_t make_sw64_kmajor_desc(uint32_t smem_addr) {
   return d;
 }
 
-template <bool kRes>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kScanThreads, 1)
+template <bool kRes, int kHalves>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * kHalves, 1)
 scan2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
              const __grid_constant__ CUtensorMap tmap_pf, const ScanParams p, const int n_stages_s) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -116,7 +116,7 @@ scan2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tail->tmem_full[a]), 1);
-      mbar_init(smem_u32(&tail->tmem_empty[a]), 8);
+      mbar_init(smem_u32(&tail->tmem_empty[a]), 8 * kHalves);   // one arrive per epilogue warp of both CTAs
     }
     mbar_init(smem_u32(&tail->a_full), 1);
     fence_barrier_init();
@@ -229,7 +229,8 @@ scan2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     }
   } else {
     // ===================== epilogue: thread <-> query (both CTAs) =====================
-    run_epilogue<true>(p, tail->invc, tail->tmem_full, tail->tmem_empty, tmem_base, qb, r, rank, t0, t1, warp, lane);
+    run_epilogue<true, kHalves>(p, tail->invc, tail->tmem_full, tail->tmem_empty, tmem_base, qb, r, rank, t0, t1,
+                                     warp, lane);
   }
 
   tc_fence_before();
@@ -438,28 +439,33 @@ bool scan2_resident_fits(int dpad) {
 // p.QB counts 256-query blocks, p.R CTA pairs per block; grid = 2 * QB * R CTAs.
 // streamed: tmap_c has 128-row x 64-col boxes (SWIZZLE_128B); resident: the same, or 128-row x 32-col
 // (SWIZZLE_64B) when built with RBK_RES_K=32.
+template <bool kRes, int kHalves>
+static cudaError_t launch_scan2_t(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const CUtensorMap& tmap_pf,
+                                  const ScanParams& p, size_t smem, int n_stages, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(scan2_kernel<kRes, kHalves>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  scan2_kernel<kRes, kHalves><<<2 * p.QB * p.R, 64 + 128 * kHalves, smem, stream>>>(tmap_q, tmap_c, tmap_pf, p, n_stages);
+  return cudaGetLastError();
+}
+
+// halves: 1 = four epilogue warps per CTA, 2 = eight (two lists per unit and query; see run_epilogue).
 cudaError_t launch_scan2(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const CUtensorMap& tmap_pf,
-                         const ScanParams& p, bool resident, cudaStream_t stream, int* ring_stages_out) {
-  cudaError_t e;
-  int n_stages = kStagesS;
+                         const ScanParams& p, bool resident, int halves, cudaStream_t stream, int* ring_stages_out) {
   if (resident) {
     const size_t smem = static_cast<size_t>(p.num_kb) * kPanelBytes + static_cast<size_t>(kStagesR) * kStageRBytes +
                         sizeof(SmemTail2);
-    e = cudaFuncSetAttribute(scan2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    scan2_kernel<true><<<2 * p.QB * p.R, kScanThreads, smem, stream>>>(tmap_q, tmap_c, tmap_pf, p, n_stages);
-  } else {
-    // 7 stages fill the 227 KB exactly (no alignment slack): only when the dynamic smem base is 1024-aligned on
-    // this device/driver (probed once); otherwise 6 stages + 1 KB of slack
-    n_stages = smem_base_is_aligned() ? kStagesS : kStagesS - 1;
-    size_t smem = static_cast<size_t>(n_stages) * kStageSBytes + sizeof(SmemTail2);
-    if (smem + 1024 <= kMaxSmem) smem += 1024;
-    e = cudaFuncSetAttribute(scan2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    scan2_kernel<false><<<2 * p.QB * p.R, kScanThreads, smem, stream>>>(tmap_q, tmap_c, tmap_pf, p, n_stages);
-    if (ring_stages_out) *ring_stages_out = n_stages;
+    return halves == 2 ? launch_scan2_t<true, 2>(tmap_q, tmap_c, tmap_pf, p, smem, kStagesS, stream)
+                       : launch_scan2_t<true, 1>(tmap_q, tmap_c, tmap_pf, p, smem, kStagesS, stream);
   }
-  return cudaGetLastError();
+  // 7 stages fill the 227 KB exactly (no alignment slack): only when the dynamic smem base is 1024-aligned on
+  // this device/driver (probed once); otherwise 6 stages + 1 KB of slack
+  const int n_stages = smem_base_is_aligned() ? kStagesS : kStagesS - 1;
+  size_t smem = static_cast<size_t>(n_stages) * kStageSBytes + sizeof(SmemTail2);
+  if (smem + 1024 <= kMaxSmem) smem += 1024;
+  if (ring_stages_out) *ring_stages_out = n_stages;
+  return halves == 2 ? launch_scan2_t<false, 2>(tmap_q, tmap_c, tmap_pf, p, smem, n_stages, stream)
+                     : launch_scan2_t<false, 1>(tmap_q, tmap_c, tmap_pf, p, smem, n_stages, stream);
 }
 
 // Hybrid launch: res_kb resident query panels + n_slots ring slots (16 KB each) must fit 227 KB.
