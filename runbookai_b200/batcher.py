@@ -93,13 +93,18 @@ class MicroBatcher:
             k_fetch = 2 * max(top_ks)
             if k_fetch > RBK_MAX_K_FETCH:
                 raise ValueError(f"topK {max(top_ks)}: the engine returns at most {RBK_MAX_K_FETCH} (= 2*topK) per query")
-            slots, scores, counts, _ = st._index.search(qvec, k_fetch, min(mins))
+            with st._st.lock:   # scan and slot -> id lookup against the same table (the index may be shared)
+                slots, scores, counts, _ = st._index.search(qvec, k_fetch, min(mins))
+                picked = []
+                for i in range(len(batch)):
+                    n = int(counts[i])
+                    keep = scores[i, :n] >= mins[i]                  # this caller's `>= minScore`
+                    s_i, v_i = slots[i, :n][keep][: 2 * top_ks[i]], scores[i, :n][keep][: 2 * top_ks[i]]
+                    picked.append(([st._ids[int(s)] for s in s_i], v_i))
             self.batches += 1
             for i, (_, o, fut) in enumerate(batch):
-                n = int(counts[i])
-                keep = scores[i, :n] >= mins[i]                      # this caller's `>= minScore`
-                s_i, v_i = slots[i, :n][keep][: 2 * top_ks[i]], scores[i, :n][keep][: 2 * top_ks[i]]
-                fut.set_result(st._hydrate(s_i, v_i, top_ks[i], o.get("typeFilter") or o.get("type_filter"),
+                ids_i, v_i = picked[i]
+                fut.set_result(st._hydrate(ids_i, v_i, top_ks[i], o.get("typeFilter") or o.get("type_filter"),
                                            o.get("serviceFilter") or o.get("service_filter")))
                 self.served += 1
         except Exception as exc:  # every waiter gets the error its own search() would have raised

@@ -11,6 +11,14 @@ here.  Steps a4 (SQL fetch, filters, final cut, vector-store.ts:223-279) stay on
 
 The reference's methods are async only because of embedText (network); this mirror is
 synchronous and adds the batched entry point `search_batch` the reference lacks.
+
+Shared index.  The reference builds a VectorStore - and re-parses every BLOB into the
+Map - at each createRetriever() call site (e.g. hook-handlers.ts:329-337 opens and closes one per hook).
+With the corpus on a GPU that would be an upload per call, so `shared=True` (the default of
+create_vector_store) keeps ONE device index and slot table per (real path of the db, device) in this
+process, reference-counted: the first opener loads it, later openers attach in O(1), the last close()
+frees it.  Instances sharing an index see each other's mutations at once (the reference's copies only
+converge at the next reload); each instance still owns its SQLite connection.
 """
 from __future__ import annotations
 
@@ -74,8 +82,33 @@ def buffer_to_float_array(buf: bytes) -> np.ndarray:
     return np.frombuffer(buf, dtype="<f8")
 
 
+class _IndexState:
+    """What replaces the reference's `embeddings: Map<string, number[]>`: the device index plus the
+    slot <-> id table.  One per VectorStore, or one per (db path, device) when shared."""
+
+    def __init__(self, key=None):
+        self.key = key                       # registry key, None = private
+        self.refs = 1
+        self.loaded = False
+        self.lock = threading.RLock()        # serialises mutation / table reads across sharing instances
+        self.index: Index | None = None
+        self.ids: list[str | None] = []      # slot -> id (None = deleted)
+        self.slot_of: dict[str, int] = {}    # live id -> slot  (the reference's Map keys)
+        self.ragged = False                  # stored rows of differing length -> search throws (S2)
+
+
+_SHARED: dict[tuple[str, int], _IndexState] = {}
+_SHARED_LOCK = threading.Lock()
+
+
+def shared_index_count() -> int:
+    """Device indexes currently kept alive by the per-path registry (introspection / tests)."""
+    with _SHARED_LOCK:
+        return len(_SHARED)
+
+
 class VectorStore:
-    def __init__(self, db_path: str, device: int | None = None, index_factory=None):
+    def __init__(self, db_path: str, device: int | None = None, index_factory=None, shared: bool = False):
         # index_factory(dim, device) -> object with the _native.Index surface; tests inject a
         # CPU stand-in to exercise the host logic where there is no GPU
         # keep_f64: the reference stores float64 embeddings; keep them so the re-rank is exact for any input
@@ -85,12 +118,48 @@ class VectorStore:
         self.db.row_factory = sqlite3.Row
         self._db_lock = threading.RLock()
         self.device = int(os.environ.get("RUNBOOK_KNN_DEVICE", "0")) if device is None else device
-        self._index: Index | None = None
-        self._ids: list[str | None] = []      # slot -> id (None = deleted)
-        self._slot_of: dict[str, int] = {}    # live id -> slot  (the reference's Map keys)
-        self._ragged = False                  # stored rows of differing length -> search throws (S2)
+        self._closed = False
         self._init_schema()
-        self._load_embeddings()
+        if shared and db_path != ":memory:" and not db_path.startswith("file:"):
+            key = (os.path.realpath(db_path), self.device)
+            with _SHARED_LOCK:
+                st = _SHARED.get(key)
+                if st is None:
+                    st = _SHARED[key] = _IndexState(key)
+                else:
+                    st.refs += 1
+            self._st = st
+        else:
+            self._st = _IndexState()
+        with self._st.lock:                  # a second opener waits for the first one's load
+            if not self._st.loaded:
+                self._load_embeddings()
+                self._st.loaded = True
+
+    # the state lives in self._st so that instances on the same db can share it
+    @property
+    def _index(self):
+        return self._st.index
+
+    @_index.setter
+    def _index(self, v):
+        self._st.index = v
+
+    @property
+    def _ids(self):
+        return self._st.ids
+
+    @property
+    def _slot_of(self):
+        return self._st.slot_of
+
+    @property
+    def _ragged(self):
+        return self._st.ragged
+
+    @_ragged.setter
+    def _ragged(self, v):
+        self._st.ragged = v
 
     # ------------------------------------------------------------------ setup
     def _init_schema(self) -> None:
@@ -146,11 +215,13 @@ class VectorStore:
         text = "\n\n".join(p for p in [document_title, chunk.get("sectionTitle"), chunk["content"]] if p)
         embedding = _emb.embed_text(text)
         vid = f"vec_{chunk['id']}"
-        with self.db:
-            self.db.execute(self._INSERT, (vid, chunk["id"], chunk["documentId"], float_array_to_buffer(embedding),
-                                           chunk["content"], chunk.get("sectionTitle") or document_title, type,
-                                           json.dumps(list(services), separators=(",", ":"))))
-        self._set(vid, embedding)
+        with self._st.lock, self._db_lock:
+            with self.db:
+                self.db.execute(self._INSERT, (vid, chunk["id"], chunk["documentId"],
+                                               float_array_to_buffer(embedding), chunk["content"],
+                                               chunk.get("sectionTitle") or document_title, type,
+                                               json.dumps(list(services), separators=(",", ":"))))
+            self._set(vid, embedding)
 
     def add_chunks(self, chunks: Sequence[dict]) -> None:
         """vector-store.ts:135-183.  chunks: [{chunk, documentTitle, type, services}]."""
@@ -159,6 +230,10 @@ class VectorStore:
         texts = ["\n\n".join(p for p in [c["documentTitle"], c["chunk"].get("sectionTitle"), c["chunk"]["content"]]
                              if p) for c in chunks]
         embeddings = _emb.embed_texts(texts)
+        with self._st.lock, self._db_lock:
+            self._add_embedded(chunks, embeddings)
+
+    def _add_embedded(self, chunks, embeddings) -> None:
         with self.db:  # one transaction
             for c, e in zip(chunks, embeddings):
                 ch = c["chunk"]
@@ -191,6 +266,10 @@ class VectorStore:
 
     def delete_document(self, document_id: str) -> None:
         """vector-store.ts:285-297."""
+        with self._st.lock, self._db_lock:
+            self._delete_document(document_id)
+
+    def _delete_document(self, document_id: str) -> None:
         rows = self.db.execute("SELECT id FROM vector_embeddings WHERE document_id = ?", (document_id,)).fetchall()
         slots = []
         for r in rows:
@@ -214,20 +293,35 @@ class VectorStore:
 
     def clear(self) -> None:
         """vector-store.ts:322-325."""
-        with self.db:
-            self.db.execute("DELETE FROM vector_embeddings")
-        self._ids.clear()
-        self._slot_of.clear()
-        self._ragged = False
-        if self._index is not None:
-            self._index.clear()
+        with self._st.lock, self._db_lock:
+            with self.db:
+                self.db.execute("DELETE FROM vector_embeddings")
+            self._ids.clear()
+            self._slot_of.clear()
+            self._ragged = False
+            if self._index is not None:
+                self._index.clear()
 
     def close(self) -> None:
-        """vector-store.ts:330-332."""
+        """vector-store.ts:330-332.  The device index goes with the LAST instance that shares it."""
+        if self._closed:
+            return
+        self._closed = True
         self.db.close()
-        if self._index is not None:
-            self._index.close()
-            self._index = None
+        st = self._st
+        if st.key is not None:
+            with _SHARED_LOCK:
+                st.refs -= 1
+                last = st.refs == 0
+                if last:
+                    _SHARED.pop(st.key, None)
+        else:
+            last = True
+        if last:
+            with st.lock:
+                if st.index is not None:
+                    st.index.close()
+                    st.index = None
 
     # ------------------------------------------------------------------ search
     def search(self, query: str, options: dict | None = None, **kw) -> list[RetrievedChunk]:
@@ -248,18 +342,21 @@ class VectorStore:
             raise ValueError(f"topK {top_k}: the engine returns at most {RBK_MAX_K_FETCH} (= 2*topK) per query")
         q = np.asarray(_emb.embed_texts(list(queries)) if len(queries) > 1 else [_emb.embed_text(queries[0])],
                        dtype=np.float64)                              # :205
-        if self._index is None or not self._ids:
-            return [[] for _ in queries]
-        if self._ragged or q.shape[1] != self._index.dim:
-            raise DimensionError(RBK_EDIM, "Vectors must have the same length")   # embedder.ts:170
-        # :207-221 — scan, `>= minScore`, stable sort desc, first 2*topK: one device call
-        slots, scores, counts, _ = self._index.search(q, 2 * top_k, min_score)
-        return [self._hydrate(slots[b, :counts[b]], scores[b, :counts[b]], top_k, type_filter, service_filter)
+        with self._st.lock:   # the slot table must be the one the scan ran against
+            if self._index is None or not self._ids:
+                return [[] for _ in queries]
+            if self._ragged or q.shape[1] != self._index.dim:
+                raise DimensionError(RBK_EDIM, "Vectors must have the same length")   # embedder.ts:170
+            # :207-221 — scan, `>= minScore`, stable sort desc, first 2*topK: one device call
+            slots, scores, counts, _ = self._index.search(q, 2 * top_k, min_score)
+            ids = [[self._ids[int(s)] for s in slots[b, :counts[b]]] for b in range(len(queries))]
+        return [self._hydrate(ids[b], scores[b, :counts[b]], top_k, type_filter, service_filter)
                 for b in range(len(queries))]
 
-    def _hydrate(self, slots, scores, top_k, type_filter, service_filter) -> list[RetrievedChunk]:
+    def _hydrate(self, top_ids, scores, top_k, type_filter, service_filter) -> list[RetrievedChunk]:
         """vector-store.ts:223-279 (a4): stays on the host."""
-        top_ids = [self._ids[int(s)] for s in slots]
+        pairs = [(i, float(sc)) for i, sc in zip(top_ids, scores) if i is not None]   # None: deleted meanwhile
+        top_ids = [i for i, _ in pairs]
         if not top_ids:
             return []                                                 # :223-225
         sql = ("SELECT id, chunk_id, document_id, content, title, type, services FROM vector_embeddings "
@@ -270,7 +367,7 @@ class VectorStore:
             params += list(type_filter)
         with self._db_lock:
             rows = self.db.execute(sql, params).fetchall()
-        score_map = {i: float(s) for i, s in zip(top_ids, scores)}
+        score_map = dict(pairs)
         results: list[RetrievedChunk] = []
         for row in rows:
             services = json.loads(row["services"] or "[]")
@@ -287,9 +384,13 @@ class VectorStore:
     getCount, hasDocument = get_count, has_document
 
 
-def create_vector_store(base_dir: str = ".runbook", device: int | None = None, index_factory=None) -> VectorStore:
-    """vector-store.ts:338-341."""
-    return VectorStore(f"{base_dir}/vectors.db", device, index_factory)
+def create_vector_store(base_dir: str = ".runbook", device: int | None = None, index_factory=None,
+                        shared: bool | None = None) -> VectorStore:
+    """vector-store.ts:338-341.  shared (default on; RUNBOOK_KNN_SHARED_INDEX=0 turns it off): call sites
+    that build and close a store per use attach to the process-wide index of that db instead of re-uploading."""
+    if shared is None:
+        shared = os.environ.get("RUNBOOK_KNN_SHARED_INDEX", "1") != "0"
+    return VectorStore(f"{base_dir}/vectors.db", device, index_factory, shared=shared)
 
 
 createVectorStore = create_vector_store

@@ -211,3 +211,38 @@ def test_micro_batcher_coalesces_and_matches_individual_searches(store):
     mb.close()
     assert got == want
     assert mb.served == len(asks) and mb.batches <= 3        # 30 concurrent calls -> a handful of passes
+
+
+def test_shared_index_is_refcounted_per_db_path(tmp_path):
+    """call sites that build and close a store per use (hook-handlers.ts:329-337) attach to ONE
+    index per db path; the last close frees it; mutations through any instance are seen by all."""
+    from runbookai_b200 import embedder
+    from runbookai_b200.vector_store import VectorStore, create_vector_store, shared_index_count
+    embedder.configure(HashEmbedder(64))
+    made = []
+
+    def factory(d, dev):
+        made.append(OracleIndex(d))
+        return made[-1]
+    base = str(tmp_path)
+    a = create_vector_store(base, index_factory=factory)
+    a.add_chunks(_chunks(6, "doc1", "runbook", ("api",)))
+    b = create_vector_store(base, index_factory=factory)           # attaches: no second index, no reload
+    assert len(made) == 1 and shared_index_count() == 1 and b._index is a._index
+    b.add_chunks(_chunks(4, "doc2", "postmortem", ("db",), text="postgres replication lag"))
+    q = "postgres replication lag"
+    assert [r.id for r in a.search(q, {"minScore": 0.2})] == [r.id for r in b.search(q, {"minScore": 0.2})] != []
+    a.delete_document("doc2")                                       # seen by b at once
+    assert all(r.documentId != "doc2" for r in b.search(q, {"minScore": 0.05}))
+    a.close()
+    a.close()                                                       # idempotent, does not drop b's reference
+    assert shared_index_count() == 1 and b.search("redis connection pool", {"minScore": 0.2})
+    b.close()
+    assert shared_index_count() == 0
+    c = create_vector_store(base, index_factory=factory)           # fresh load from SQLite, rowid order
+    assert len(made) == 2 and c.get_count() == 6 and len(c._ids) == 6
+    private = VectorStore(str(tmp_path / "vectors.db"), index_factory=factory)   # constructor default: private
+    assert len(made) == 3 and private._index is not c._index and shared_index_count() == 1
+    private.close()
+    c.close()
+    embedder.reset()
