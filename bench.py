@@ -169,6 +169,8 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("RBK_BENCH_WORKLOAD", "cfg3"), choices=sorted(WORKLOADS))
     ap.add_argument("--rows", type=int, default=0, help="override N_docs (debug only; marks the run reduced)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--min-score", type=float, default=None,
+                    help="cosine threshold (the reference's default is 0.5); default: none (-inf), the headline runs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = list(WORKLOADS[args.workload])
@@ -219,7 +221,7 @@ def main():
 
     # ---------------- value: batch resident in HBM ----------------
     for _ in range(args.warmup):
-        searcher.search_device(q_dev, k_fetch, None)
+        searcher.search_device(q_dev, k_fetch, args.min_score)
     launches0 = ix.stats()["kernel_launches"]
     barrier()
     t_region0 = time.monotonic()
@@ -227,7 +229,7 @@ def main():
     scan_ms = []
     ev0.record(stream)
     for _ in range(args.steps):
-        searcher.search_device(q_dev, k_fetch, None)
+        searcher.search_device(q_dev, k_fetch, args.min_score)
         scan_ms.append(ix.stats()["last_scan_ms"])
     ev1.record(stream)
     barrier()
@@ -246,8 +248,8 @@ def main():
     # ---------------- e2e: host buffers through the public call ----------------
     def e2e_step():
         if world == 1:
-            return ix.search(q_host.numpy(), k_fetch, None)      # rbk_index_search_f32: H2D + D2H inside
-        return searcher.search(q_host, k_fetch, None, device)
+            return ix.search(q_host.numpy(), k_fetch, args.min_score)      # rbk_index_search_f32: H2D + D2H inside
+        return searcher.search(q_host, k_fetch, args.min_score, device)
     for _ in range(args.warmup):
         e2e_step()
     barrier()
@@ -293,7 +295,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": desc + (" [REDUCED rows: debug run]" if reduced else ""), "n_docs": n, "dim": d,
-                       "batch": B, "k": k, "k_fetch": k_fetch, "min_score": None,
+                       "batch": B, "k": k, "k_fetch": k_fetch, "min_score": args.min_score,
                        "parallelism": f"rows sharded over {world} GPU(s), all-gather of top-k" if world > 1 else "1 GPU",
                        "rerank": "exact fp64 re-rank of k' candidates, ids/scores identical to the fp64 oracle",
                        "l2": f"corpus {2.0 * n_local * d / 1e9:.1f} GB per GPU >> 126 MB L2, no flush needed",
