@@ -346,13 +346,12 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
 #endif
   int as = 0;
   uint32_t aph = 0;
-  // the next tile's 1/||c|| travels in registers while this tile is processed (hides its L2/HBM latency)
-  // 1/||c|| of a tile's 256 rows are staged in shared memory, one 128-thread barrier per tile (the four
-  // epilogue warps wait for the slowest of the previous tile there).  -DRBK_NORMS_L1 builds the alternative
-  // that was tried to get rid of that barrier - every warp reads the norms straight from the array through
-  // L1 with uniform 16-byte loads, next tile prefetched - and measured 15-25 % SLOWER on B200 (cfg2 scan
-  // 0.34 -> 0.42 ms, B=1024 x 4M rows 4.87 -> 5.43 ms): the L1 round trip of 8 loads per chunk costs more
-  // than the barrier wait it removes.
+  // 1/||c|| of a tile's 256 rows are staged in shared memory behind one barrier of all epilogue threads per
+  // tile (the warps wait there for the slowest of the previous tile); the NEXT tile's values travel in registers
+  // while this one is processed, which hides their L2/HBM latency.  -DRBK_NORMS_L1 builds the alternative that
+  // was tried to get rid of the barrier - every warp reads the norms straight from the array through L1 with
+  // uniform 16-byte loads, next tile prefetched - and measured 15-25 % SLOWER on B200 (cfg2 scan 0.34 -> 0.42 ms,
+  // B=1024 x 4M rows 4.87 -> 5.43 ms): the L1 round trip of 8 loads per chunk costs more than the barrier wait.
 #ifndef RBK_NORMS_L1
   constexpr bool kGN = false;
   float nx0 = 0.f, nx1 = 0.f;
