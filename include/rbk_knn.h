@@ -142,7 +142,7 @@ rbk_status rbk_merge_topk_packed_device(int32_t device, void* cuda_stream, int32
 typedef struct {
   int64_t searches;         /* search calls */
   int64_t queries;          /* queries answered */
-  int64_t fallback_queries; /* queries re-answered by the exhaustive fp64 kernel */
+  int64_t fallback_queries; /* queries re-answered by the exhaustive fp64 kernel (after the wide retry) */
   int64_t scan_launches;    /* launches of the fused scan kernel */
   int64_t kernel_launches;  /* all kernel launches made by this index */
   float last_scan_ms;       /* device time of the scan kernel(s) of the last search */
@@ -150,7 +150,7 @@ typedef struct {
   int32_t last_kprime;      /* candidates kept per query by the last scan */
   int32_t sm_count;
   int32_t last_ring_stages; /* smem ring depth of the last scan kernel (pair kernel: 7, or 6 if the smem base is unaligned) */
-  int32_t reserved;
+  int32_t retry_batches;    /* batches scanned a second time with the widest candidate margin after a failed proof */
 } rbk_stats;
 rbk_status rbk_index_stats(const rbk_index* idx, rbk_stats* out);
 

@@ -42,7 +42,7 @@ class RbkStats(C.Structure):
         ("searches", C.c_int64), ("queries", C.c_int64), ("fallback_queries", C.c_int64),
         ("scan_launches", C.c_int64), ("kernel_launches", C.c_int64), ("last_scan_ms", C.c_float),
         ("last_total_ms", C.c_float), ("last_kprime", C.c_int32), ("sm_count", C.c_int32),
-        ("last_ring_stages", C.c_int32), ("reserved", C.c_int32),
+        ("last_ring_stages", C.c_int32), ("retry_batches", C.c_int32),
     ]
 
 

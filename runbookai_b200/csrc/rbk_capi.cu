@@ -156,6 +156,8 @@ struct rbk_index {
   CUtensorMap tmap_c, tmap_c_half, tmap_c_half32, tmap_c_pf, tmap_c_r32;
   int perf_probe = 0;
   int max_lead_tiles = kMaxLeadTiles;
+  int kprime_override = 0;   // > 0 while a batch is re-scanned with the widest candidate margin
+  bool retry_wide = true;    // RBK_KNN_RETRY_WIDE=0: failed proofs go straight to the exhaustive kernel
   int epi_halves = 0;        // 0 = default (2); RBK_KNN_HALVES=1|2 forces
   int hybrid_res_kb = -1, hybrid_slots = 8;   // -1: hybrid pair kernel off
   bool use_ts = false;  // pair kernel with queries in TMEM (dim <= 768): correct but not yet faster
@@ -289,6 +291,7 @@ rbk_status append_rows(rbk_index* ix, const void* src, bool is_device, int elem,
 }
 
 int pick_kprime(const rbk_index* ix, int k_fetch) {
+  if (ix->kprime_override > 0) return ix->kprime_override;
   int kp = static_cast<int>(round_up(k_fetch + ix->margin, 16));
   return std::min(kp, kMaxKPrime);
 }
@@ -551,6 +554,25 @@ rbk_status search_core(rbk_index* ix, const void* q_host, const void* q_dev, int
   std::vector<int> fails;
   for (int b = 0; b < B; ++b)
     if (h_flags[b]) fails.push_back(b);
+  if (!fails.empty() && ix->retry_wide && ix->stats.last_kprime < kMaxKPrime) {
+    // A proof fails when more rows tie with the k_fetch-th hit (within the scan's error bound) than the
+    // candidate margin holds - duplicated chunks, typically.  Before paying an exhaustive fp64 pass per failing
+    // query, scan the batch once more at scan speed with the widest margin (k' = 128): groups of up to ~100
+    // near-ties then fit among the candidates and the proof goes through.  Results of the queries that had
+    // already passed are recomputed to the same values (both passes are exact).
+    ix->kprime_override = kMaxKPrime;
+    st = run_scan(ix, d_q, elem == 8 ? 0 : 1, B, k_fetch, min_score, d_slots, d_scores, d_counts, d_flags, nullptr,
+                  &evc);
+    ix->kprime_override = 0;
+    if (st != RBK_OK) return st;
+    CK(copy_back());
+    CK(cudaEventRecord(get_event(ix, 1), ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+    ix->stats.retry_batches++;
+    fails.clear();
+    for (int b = 0; b < B; ++b)
+      if (h_flags[b]) fails.push_back(b);
+  }
   if (!fails.empty()) {
     st = run_fallback(ix, fails, k_fetch, min_score, d_slots, d_scores, d_counts);
     if (st != RBK_OK) return st;
@@ -619,6 +641,7 @@ rbk_status rbk_index_create_ex(int32_t dim, int32_t device, int64_t capacity_hin
   if (const char* m = getenv("RBK_KNN_RESIDENT")) ix->force_streamed = atoi(m) == 0;   // experiments only
   if (const char* m = getenv("RBK_KNN_TS")) ix->use_ts = atoi(m) != 0;
   if (const char* m = getenv("RBK_KNN_MAX_LEAD")) ix->max_lead_tiles = std::max(1, atoi(m));
+  if (const char* m = getenv("RBK_KNN_RETRY_WIDE")) ix->retry_wide = atoi(m) != 0;
   if (const char* m = getenv("RBK_KNN_HALVES")) ix->epi_halves = std::max(0, atoi(m));
   if (const char* m = getenv("RBK_KNN_PERF_PROBE")) ix->perf_probe = atoi(m);   // breaks results; timing only
   if (const char* m = getenv("RBK_KNN_HYBRID_KB")) ix->hybrid_res_kb = atoi(m);

@@ -109,8 +109,27 @@ def test_exact_ties_and_the_exhaustive_fallback(rb, oracle_mod):
         ix.append_bf16(corpus)
         s, v, c = check_against_oracle(oracle_mod, ix, corpus, q, 20, 0.5)
         assert s[0, :20].tolist() == sorted(dup_slots.tolist())[:20]
-        assert ix.stats()["fallback_queries"] >= 1
+        assert ix.stats()["fallback_queries"] >= 1 and ix.stats()["retry_batches"] >= 1   # 200 ties > 128 candidates
         check_against_oracle(oracle_mod, ix, corpus, q, 112, None)
+
+
+def test_moderate_tie_groups_are_settled_by_the_wide_rescan(rb, oracle_mod):
+    """70 duplicated rows tie across a 48-candidate boundary: the first proof fails, one more scan with
+    k' = 128 holds the whole tie group and proves the answer - no exhaustive pass."""
+    from runbookai_b200 import synth
+    n, d = 20000, 128
+    corpus = synth.random_corpus(n, d, 17)
+    q = synth.random_queries(5, d, 18)
+    dup_slots = np.random.default_rng(19).choice(n, 70, replace=False)
+    corpus[dup_slots] = synth.f32_to_bf16_bits(q[1] * 0.25)
+    with rb.Index(d) as ix:
+        ix.append_bf16(corpus)
+        s, v, c = check_against_oracle(oracle_mod, ix, corpus, q, 20, None)
+        assert s[1, :20].tolist() == sorted(dup_slots.tolist())[:20]
+        st = ix.stats()
+        assert st["retry_batches"] >= 1 and st["fallback_queries"] == 0
+        check_against_oracle(oracle_mod, ix, corpus, q, 20, 0.5)
+        assert ix.stats()["fallback_queries"] == 0
 
 
 def test_input_formats_agree_and_rows_read_back(rb, oracle_mod):
