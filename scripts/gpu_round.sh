@@ -7,6 +7,7 @@ echo "== smoke"; timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -3 | 
 echo "== bench cfg3"; timeout 900 python bench.py 2>gpurun_out/bench_cfg3.err | tee gpurun_out/bench_cfg3.json
 echo "== bench cfg2"; timeout 600 python bench.py --workload cfg2 --steps 50 2>gpurun_out/bench_cfg2.err | tee gpurun_out/bench_cfg2.json
 echo "== bench cfg1"; timeout 600 python bench.py --workload cfg1 --steps 200 2>gpurun_out/bench_cfg1.err | tee gpurun_out/bench_cfg1.json
+echo "== bench cfg5"; timeout 600 python bench.py --workload cfg5 --steps 30 --no-cpu-baseline 2>gpurun_out/bench_cfg5.err | tee gpurun_out/bench_cfg5.json
 echo "== scan timings"; timeout 300 python scripts/gpu_check.py time1 time2 time3 sweep1 2>&1 | tail -12 | tee gpurun_out/timings.log
 echo "== bench reference"; timeout 600 python bench.py --impl reference --steps 5 --warmup 1 2>gpurun_out/bench_ref.err | tee gpurun_out/bench_ref.json
 if [ "$1" != "noncu" ]; then
