@@ -93,7 +93,25 @@ class KnowledgeStore:
                                content=r["content"], type=r["type"], services=json.loads(r["services"] or "[]"),
                                score=abs(r["score"]), sourceUrl=r["source_url"] or None) for r in rows]
 
+    def has_document(self, doc_id: str) -> bool:
+        """`getDocument(id) !== null` (sqlite.ts:261-265)."""
+        return self.db.execute("SELECT 1 FROM documents WHERE id = ?", (doc_id,)).fetchone() is not None
+
+    def get_document_count(self) -> int:
+        """sqlite.ts:313-317."""
+        return self.db.execute("SELECT COUNT(*) FROM documents").fetchone()[0]
+
+    def get_document_counts_by_type(self) -> dict:
+        """sqlite.ts:233-255."""
+        counts = {t: 0 for t in ("runbook", "postmortem", "architecture", "ownership", "known_issue", "environment",
+                                 "playbook", "faq")}
+        for r in self.db.execute("SELECT type, COUNT(*) AS count FROM documents GROUP BY type"):
+            if r["type"] in counts:
+                counts[r["type"]] = r["count"]
+        return counts
+
     def close(self) -> None:
         self.db.close()
 
-    upsertDocument = upsert_document
+    upsertDocument, hasDocument = upsert_document, has_document
+    getDocumentCount, getDocumentCountsByType = get_document_count, get_document_counts_by_type

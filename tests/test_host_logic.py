@@ -246,3 +246,36 @@ def test_shared_index_is_refcounted_per_db_path(tmp_path):
     private.close()
     c.close()
     embedder.reset()
+
+
+def test_knowledge_retriever_sync_mirrors_documents_into_the_vector_store(tmp_path):
+    """retriever/index.ts:44-126 with the sync hook of SURVEY §8f-2: documents land in the FTS store AND in the
+    vector store; an updated document replaces its old vectors; search buckets chunks by type."""
+    from runbookai_b200 import embedder
+    from runbookai_b200.retriever import KnowledgeRetriever
+    from runbookai_b200.vector_store import VectorStore
+    embedder.configure(HashEmbedder(64))
+
+    def doc(did, typ, text, n=3, services=("api",)):
+        return {"id": did, "type": typ, "title": did.upper(), "services": list(services),
+                "chunks": [{"id": f"{did}_{i}", "content": f"{text} step {i}", "sectionTitle": f"S{i}"} for i in range(n)]}
+    batch = [[doc("d1", "runbook", "redis connection pool exhausted restart the pool"),
+              doc("d2", "postmortem", "postgres replication lag after failover", services=("db",)),
+              doc("d3", "known_issue", "kubernetes pod crashloop out of memory")]]
+    vs = VectorStore(str(tmp_path / "vectors.db"), index_factory=lambda d, dev: OracleIndex(d))
+    r = KnowledgeRetriever({"storePath": str(tmp_path / "knowledge.db"), "sources": [lambda since: batch[0]]},
+                           vector_store=vs)
+    assert r.sync() == {"added": 3, "updated": 0}
+    assert r.get_document_count() == 3 and vs.get_count() == 9 and r.get_document_counts_by_type()["runbook"] == 1
+    k = r.search("redis connection pool")
+    assert set(k) == {"runbooks", "postmortems", "architecture", "knownIssues"}
+    assert k["runbooks"] and all(c.documentId == "d1" for c in k["runbooks"])
+    assert r.get_runbooks_for_service("api")["postmortems"] == []
+    # an update with fewer chunks: the old vectors of d1 must be gone, not just overwritten
+    batch[0] = [doc("d1", "runbook", "redis sentinel failover procedure", n=2)]
+    assert r.sync() == {"added": 0, "updated": 1}
+    assert vs.get_count() == 8 and not any(i == "vec_d1_2" for i in vs._ids if i)
+    hits = vs.search("redis sentinel failover procedure", {"minScore": 0.2})
+    assert hits and hits[0].documentId == "d1"
+    r.close()
+    embedder.reset()
