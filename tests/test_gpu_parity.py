@@ -132,6 +132,30 @@ def test_moderate_tie_groups_are_settled_by_the_wide_rescan(rb, oracle_mod):
         assert ix.stats()["fallback_queries"] == 0
 
 
+def test_multi_device_index_single_process(rb, oracle_mod):
+    """multi_device.py on real indexes: one host process, rows dealt block-cyclically over two device indexes
+    (two GPUs when the box has them, else both on GPU 0), host merge == the oracle on the whole corpus."""
+    import torch
+    from runbookai_b200 import synth
+    from runbookai_b200.multi_device import MultiDeviceIndex
+    n, d = 30_000, 256
+    corpus = synth.random_corpus(n, d, 41)
+    q = synth.random_queries(9, d, 42)
+    synth.plant_neighbours(corpus, q, 12, 43)
+    devs = [0, 1] if torch.cuda.device_count() > 1 else [0, 0]
+    with MultiDeviceIndex(d, devices=devs, block=1024) as ix:
+        for r0 in range(0, n, 7000):                       # appends that straddle blocks and devices
+            assert ix.append_bf16(corpus[r0:r0 + 7000]) == r0
+        check_against_oracle(oracle_mod, ix, corpus, q, 24, 0.5)
+        check_against_oracle(oracle_mod, ix, corpus, q, 24, None)
+        dead = np.random.default_rng(44).choice(n, 500, replace=False)
+        ix.tombstone(dead)
+        live = np.ones(n, dtype=np.uint8)
+        live[dead] = 0
+        check_against_oracle(oracle_mod, ix, corpus, q, 24, None, live=live)
+        assert ix.count() == n - 500 and ix.stats()["devices"] == 2
+
+
 def test_input_formats_agree_and_rows_read_back(rb, oracle_mod):
     from runbookai_b200 import synth
     n, d = 3000, 96

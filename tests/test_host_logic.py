@@ -279,3 +279,38 @@ def test_knowledge_retriever_sync_mirrors_documents_into_the_vector_store(tmp_pa
     assert hits and hits[0].documentId == "d1"
     r.close()
     embedder.reset()
+
+
+def test_multi_device_index_equals_one_index(oracle_mod):
+    """Single-process multi-GPU (multi_device.py) on CPU stand-ins: block-cyclic sharding over 3 'devices' gives
+    the same (slots, fp64 scores, counts) as one index, through appends that straddle blocks, an overwrite,
+    tombstones, ties across devices and a clear."""
+    from runbookai_b200 import synth
+    from runbookai_b200.multi_device import MultiDeviceIndex
+    rng = np.random.default_rng(5)
+    d = 48
+    one = OracleIndex(d)
+    multi = MultiDeviceIndex(d, devices=[0, 1, 2], block=64, index_factory=lambda dim, dev: OracleIndex(dim))
+    q = synth.random_queries(4, d, 3).astype(np.float64)                 # bf16-exact values
+    first_slots = []
+    for n in (1, 63, 64, 130, 257, 5):                                  # runs that start and end mid-block
+        rows = synth.bf16_bits_to_f32(synth.random_corpus(n, d, 100 + n)).astype(np.float64)
+        first_slots.append((one.append_f64(rows), multi.append_f64(rows)))
+    assert all(a == b for a, b in first_slots) and multi.size() == one.size() == 520
+    dup = q[0] * 0.5                                                     # exact ties on different devices
+    for s in (3, 70, 140, 300, 511):
+        one.overwrite_f64(s, dup)
+        multi.overwrite_f64(s, dup)
+    dead = rng.choice(520, 40, replace=False)
+    one.tombstone(dead)
+    multi.tombstone(dead)
+    assert multi.count() == one.count() == 480
+    for k, ms in ((8, None), (16, 0.1), (32, 0.5)):
+        a, b = one.search(q, k, ms), multi.search(q, k, ms)
+        assert (a[2] == b[2]).all() and (a[0] == b[0]).all()
+        assert np.array_equal(a[1], b[1], equal_nan=True)
+    with pytest.raises(Exception):
+        multi.search(np.zeros((1, d + 1)), 4, None)
+    multi.clear()
+    assert multi.size() == 0 and multi.search(q, 4, None)[2].tolist() == [0, 0, 0, 0]
+    multi.close()
