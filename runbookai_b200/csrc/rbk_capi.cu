@@ -156,6 +156,7 @@ struct rbk_index {
   CUtensorMap tmap_c, tmap_c_half, tmap_c_half32, tmap_c_pf, tmap_c_r32;
   int perf_probe = 0;
   int max_lead_tiles = kMaxLeadTiles;
+  int seed_tile = -1;        // -1 = by unit count; RBK_KNN_SEED_TILE=0|1 forces
   int kprime_override = 0;   // > 0 while a batch is re-scanned with the widest candidate margin
   bool retry_wide = true;    // RBK_KNN_RETRY_WIDE=0: failed proofs go straight to the exhaustive kernel
   int epi_halves = 0;        // 0 = default (2); RBK_KNN_HALVES=1|2 forces
@@ -415,6 +416,12 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
     if (pairs && !ts && ix->hybrid_res_kb < 0) {
       halves = ix->epi_halves > 0 ? std::min(ix->epi_halves, kMaxHalves) : kMaxHalves;
     }
+    // Start-up seeds (rbk_epilogue.cuh): two per thread and tile when many units feed one query's histogram
+    // (>= 4 k' seeds in total) - pair kernel only: measured in one box, B=256 scans 2 % (1M rows) to 9 % (65k
+    // rows) faster than with two seeds per 32-column chunk, but the 1-CTA kernel at B=1 became bimodal (0.03 /
+    // 0.07 ms at 65k rows): with one or two tiles per unit and only two seeds from each, a unit that reads the
+    // histogram before ~k'/2 peers have seeded finds no threshold and floods its lists.
+    sp.seed_tile = ix->seed_tile >= 0 ? ix->seed_tile : ((pairs && R * 2 * halves >= 4 * kprime) ? 1 : 0);
     if (pairs && !ts && ix->hybrid_res_kb >= 0)
       CK(launch_scan2h(tmap_q, ix->tmap_c_half, sp, ix->hybrid_res_kb, ix->hybrid_slots, ix->stream));
     else if (ts)
@@ -641,6 +648,7 @@ rbk_status rbk_index_create_ex(int32_t dim, int32_t device, int64_t capacity_hin
   if (const char* m = getenv("RBK_KNN_RESIDENT")) ix->force_streamed = atoi(m) == 0;   // experiments only
   if (const char* m = getenv("RBK_KNN_TS")) ix->use_ts = atoi(m) != 0;
   if (const char* m = getenv("RBK_KNN_MAX_LEAD")) ix->max_lead_tiles = std::max(1, atoi(m));
+  if (const char* m = getenv("RBK_KNN_SEED_TILE")) ix->seed_tile = atoi(m);
   if (const char* m = getenv("RBK_KNN_RETRY_WIDE")) ix->retry_wide = atoi(m) != 0;
   if (const char* m = getenv("RBK_KNN_HALVES")) ix->epi_halves = std::max(0, atoi(m));
   if (const char* m = getenv("RBK_KNN_PERF_PROBE")) ix->perf_probe = atoi(m);   // breaks results; timing only

@@ -160,8 +160,12 @@ __device__ __forceinline__ void filter_append(FilterState& s, float t, uint32_t 
 // 16 per unit and tile, which is where the query's best rows so far are with overwhelming probability), all
 // units' seeds then give the threshold, and the regular pass over the same accumulators appends the handful
 // of rows above it - without counting them again.
+// acc1 >= acc2: with whole_tile the two best rows seen so far in this thread's part of the tile (counted by the
+// caller after the last chunk: 2 atomics per thread instead of 2 per chunk - enough when many units feed the
+// same histogram, and an order of magnitude fewer same-line atomics in the first microseconds of a scan).
 template <bool kGlobal = false>
-__device__ __forceinline__ void seed_chunk(FilterState& s, const uint32_t (&v)[32], const float* invc32) {
+__device__ __forceinline__ void seed_chunk(FilterState& s, const uint32_t (&v)[32], const float* invc32,
+                                           bool whole_tile, float& acc1, float& acc2) {
   const float4* ic4 = reinterpret_cast<const float4*>(invc32);
   float m1 = -INFINITY, m2 = -INFINITY;
 #pragma unroll
@@ -174,6 +178,12 @@ __device__ __forceinline__ void seed_chunk(FilterState& s, const uint32_t (&v)[3
     const float x = fmaxf(fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)), -INFINITY);   // a group of dead rows: NaN -> -inf
     m2 = fmaxf(m2, fminf(m1, x));
     m1 = fmaxf(m1, x);
+  }
+  if (whole_tile) {   // merge (m1 >= m2) into (acc1 >= acc2): the two largest of the four, distinct rows
+    const float lo = fmaxf(fminf(acc1, m1), fmaxf(acc2, m2));
+    acc1 = fmaxf(acc1, m1);
+    acc2 = lo;
+    return;
   }
   if (m1 > s.thr) hist_add(s, m1);
   if (m2 > s.thr) hist_add(s, m2);
@@ -420,19 +430,26 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
 #ifdef RBK_EPI_PROFILE
       const long long t_seed = clock64();
 #endif
+      const bool seed_tile = p.seed_tile != 0;
+      float sa1 = -INFINITY, sa2 = -INFINITY;
       tmem_ld_32x32b_x32(tcol, va);
 #pragma unroll 1
       for (int c2 = 0; c2 < kCols / 64; ++c2) {
         tmem_wait_ld_dep(va);
         tmem_ld_32x32b_x32(tcol + static_cast<uint32_t>((2 * c2 + 1) * 32), vb);
-        seed_chunk<kGN>(fs, va, invc + col0 + (2 * c2) * 32);
+        seed_chunk<kGN>(fs, va, invc + col0 + (2 * c2) * 32, seed_tile, sa1, sa2);
         tmem_wait_ld_dep(vb);
         if (c2 + 1 < kCols / 64) tmem_ld_32x32b_x32(tcol + static_cast<uint32_t>((2 * c2 + 2) * 32), va);
-        seed_chunk<kGN>(fs, vb, invc + col0 + (2 * c2 + 1) * 32);
+        seed_chunk<kGN>(fs, vb, invc + col0 + (2 * c2 + 1) * 32, seed_tile, sa1, sa2);
+      }
+      if (seed_tile) {
+        if (sa1 > fs.thr) hist_add(fs, sa1);
+        if (sa2 > fs.thr) hist_add(fs, sa2);
       }
       // the other units' seeds land within a microsecond or so of ours: a few short retries when the
-      // histogram cannot hold k' rows yet but soon will (R units x 16 seeds)
-      const int tries = (p.R * 16 >= 2 * p.kprime) ? 6 : 1;
+      // histogram cannot hold k' rows yet but soon will
+      const int seeds_per_unit = seed_tile ? 2 * kHalves : 16;
+      const int tries = (p.R * seeds_per_unit >= 2 * p.kprime) ? 6 : 1;
       for (int t = 0; t < tries; ++t) {
         const bool found = filter_refresh(fs, p.kprime);
         if (__all_sync(0xFFFFFFFFu, found || !fs.valid)) break;

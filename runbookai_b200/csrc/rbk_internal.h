@@ -39,6 +39,7 @@ struct ScanParams {
   int dpad;     // padded row length (elements)
   int prefetch_tiles;  // query-resident pair kernel: L2 prefetch distance in tiles (0 = off)
   int max_lead_tiles;  // lockstep: tiles a producer may lead the slowest peer of its range
+  int seed_tile;       // start-up seeding: 1 = count each thread's two best rows of its first tile, 0 = two per chunk
   int perf_probe;      // 0 = normal.  TIMING EXPERIMENTS ONLY (results are wrong): 1 = epilogue drains TMEM but does not filter
   int QB;       // query blocks
   int R;        // corpus ranges (CTAs per query block)
