@@ -34,7 +34,7 @@ class Unit:
         self.compactions = 0
 
 
-def run_filter(scores, n_units, kprime, rng, seed_first_tile=True, publish=True):
+def run_filter(scores, n_units, kprime, rng, seed_first_tile=True, publish=True, seed_whole_tile=False):
     """scores: approximate cosine per row (one query).  Units scan disjoint contiguous ranges, interleaved tile
     by tile in a random order (units are not synchronised on the GPU either).  Returns (units, hist)."""
     n = len(scores)
@@ -81,8 +81,9 @@ def run_filter(scores, n_units, kprime, rng, seed_first_tile=True, publish=True)
             gthr = max(gthr, u.thr)
         nohist = False
         if it == 0 and seed_first_tile:                            # seeding pass: two best rows of every chunk
-            for c0 in range(0, len(rows), CHUNK):
-                ch = rows[c0:c0 + CHUNK]
+            step = len(rows) if seed_whole_tile else CHUNK         # pair kernel with many units: two per tile
+            for c0 in range(0, len(rows), step):
+                ch = rows[c0:c0 + step]
                 for r in ch[np.argsort(-scores[ch], kind="stable")[:2]]:
                     if scores[r] > u.thr:
                         hist_add(int(r))
@@ -155,8 +156,9 @@ def test_filter_thresholds_are_lower_bounds(name, kprime):
         s = np.clip(rng.normal(0, 0.3, n), -1, 1)
     s = s.astype(np.float32).astype(np.float64)
     for n_units in (1, 5):
-        for seed_first_tile, publish in ((True, True), (False, True), (True, False)):
-            units, hist = run_filter(s, n_units, kprime, rng, seed_first_tile, publish)
+        for seed_first_tile, publish, whole in ((True, True, False), (True, True, True), (False, True, False),
+                                                (True, False, False)):
+            units, hist = run_filter(s, n_units, kprime, rng, seed_first_tile, publish, whole)
             check_invariants(s, units, hist, kprime)
     if name == "ascending":              # the model does go through the compaction path
         assert any(u.compactions > 0 for u in units)
