@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define RBK_ABI_VERSION 1
+#define RBK_ABI_VERSION 2
 /* Largest k_fetch a single search accepts (the scan keeps k_fetch + margin <= 128). */
 #define RBK_MAX_K_FETCH 112
 
@@ -122,6 +122,18 @@ rbk_status rbk_index_search_device(rbk_index* idx, const void* dev_queries_f32, 
                                    double min_score, void* dev_out_slots_i64, void* dev_out_scores_f64,
                                    void* dev_out_counts_i32);
 
+/* Enqueue-only variant: nothing is synchronised, the call returns as soon as the kernels are queued on the index
+ * stream, so batches pipeline back to back and an exchange step (all-gather + rbk_merge_topk_packed_device) can be
+ * queued behind it without a host round trip in between.  dev_out_flags_i32[B]: 0 = the answer of query b is
+ * proven exact (the normal case), 1 = not proven (more near-ties around the k_fetch-th hit than the candidate
+ * margin holds).  The caller checks the flags when it eventually synchronises - for a sharded corpus AFTER the
+ * merge, whose out_flags OR the shards' flags - and re-answers a batch that has any dirty query with the
+ * synchronous rbk_index_search_device (which rescans with a wide margin / falls back to the exhaustive kernel).
+ * All four outputs may point into a packed block (below). */
+rbk_status rbk_index_search_device_async(rbk_index* idx, const void* dev_queries_f32, int32_t B, int32_t k_fetch,
+                                         double min_score, void* dev_out_slots_i64, void* dev_out_scores_f64,
+                                         void* dev_out_counts_i32, void* dev_out_flags_i32);
+
 /* Merge G per-shard result lists (layout [G][B][k_fetch], each sorted as above, device
  * memory, e.g. the output of an all-gather) into [B][k_fetch] by (score desc, slot asc).
  * Enqueued on cuda_stream; no synchronisation. */
@@ -131,12 +143,16 @@ rbk_status rbk_merge_topk_device(int32_t device, void* cuda_stream, int32_t G, i
 
 /* Same merge for G PACKED per-shard blocks laid end to end (what ONE all-gather of each rank's block
  * produces).  Block layout, rbk_packed_block_bytes(B, k_fetch) bytes: slots i64[B*k_fetch] | scores
- * f64[B*k_fetch] | counts i32[B] (padded to 16 bytes).  rbk_index_search_device can write straight into a
- * block: pass block, block + B*k_fetch*8 and block + B*k_fetch*16 as its three output pointers. */
+ * f64[B*k_fetch] | counts i32[B] (padded to 16 bytes) | flags i32[B] (padded to 16 bytes; starts at
+ * rbk_packed_flags_offset).  rbk_index_search_device(_async) can write straight into a block: pass block,
+ * block + B*k_fetch*8, block + B*k_fetch*16 (and block + rbk_packed_flags_offset for the flags).
+ * dev_out_flags_i32 (nullable): i32[B+1]; [b] = OR of the shards' flags of query b, [B] += number of dirty
+ * queries of this call (a running count the caller zeroes, so a pipelined loop checks once at the end). */
 int64_t rbk_packed_block_bytes(int32_t B, int32_t k_fetch);
+int64_t rbk_packed_flags_offset(int32_t B, int32_t k_fetch);
 rbk_status rbk_merge_topk_packed_device(int32_t device, void* cuda_stream, int32_t G, int32_t B, int32_t k_fetch,
                                         const void* dev_blocks, void* dev_out_slots_i64, void* dev_out_scores_f64,
-                                        void* dev_out_counts_i32);
+                                        void* dev_out_counts_i32, void* dev_out_flags_i32);
 
 /* ---- introspection ---- */
 typedef struct {
@@ -145,14 +161,17 @@ typedef struct {
   int64_t fallback_queries; /* queries re-answered by the exhaustive fp64 kernel (after the wide retry) */
   int64_t scan_launches;    /* launches of the fused scan kernel */
   int64_t kernel_launches;  /* all kernel launches made by this index */
-  float last_scan_ms;       /* device time of the scan kernel(s) of the last search */
+  float last_scan_ms;       /* device time of the scan kernel(s) of the last synchronous search (async: of the last finished scan) */
   float last_total_ms;      /* device time of the whole last search */
   int32_t last_kprime;      /* candidates kept per query by the last scan */
   int32_t sm_count;
   int32_t last_ring_stages; /* smem ring depth of the last scan kernel (pair kernel: 7, or 6 if the smem base is unaligned) */
   int32_t retry_batches;    /* batches scanned a second time with the widest candidate margin after a failed proof */
+  double scan_ms_total;     /* device time of all scan kernels that have FINISHED so far (CUDA events around every launch) */
+  int64_t scans_timed;      /* number of scan launches folded into scan_ms_total */
 } rbk_stats;
-rbk_status rbk_index_stats(const rbk_index* idx, rbk_stats* out);
+/* Never blocks: folds in the scans that have finished and returns. */
+rbk_status rbk_index_stats(rbk_index* idx, rbk_stats* out);
 
 /* Debug/validation aid (tests only): run the scan on `queries` (host f32, B x dim) and
  * return the approximate scores of every (query,row) pair, B x size() floats (host).

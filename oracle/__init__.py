@@ -7,8 +7,12 @@ from .oracle import (  # noqa: F401
     build,
     cosine,
     find_most_similar,
+    host_threads,
+    merge_lists,
     rrf,
     scores,
     search,
     search_batch_mt,
+    search_batch_verify,
+    search_chunked,
 )

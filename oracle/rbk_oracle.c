@@ -242,6 +242,137 @@ int64_t rbk_oracle_search_batch_bf16_mt(const uint16_t *corpus, int64_t n, int64
   return 0;
 }
 
+/* ---- "verify" variant of the batched search: the SAME per-(query,row) arithmetic, arranged so a CPU can
+ * check millions of rows in seconds.  Two rearrangements, neither of which changes a single rounding:
+ *   1. normA (query) and normB (row) are each one deterministic sequential chain (embedder.ts:179-180) whose
+ *      value does not depend on the other vector, so they are computed once per query / once per row instead
+ *      of once per pair;
+ *   2. the dot chains of 8 different queries against one row are independent of each other, so they are
+ *      advanced side by side (GCC vector extension, 2 lanes x 4 registers): every lane still does
+ *      dot = dot + q[i]*c[i] for i = 0..d-1, multiply then add, no contraction (-ffp-contract=off).
+ * tests/test_oracle.py checks it bit for bit against the literal loop above.  It is used only as the CHECKER
+ * of large GPU runs (tests, bench.py's parity leg) - never as the timed CPU baseline, which stays literal. */
+typedef double v2d __attribute__((vector_size(16)));
+
+typedef struct {
+  const uint16_t *corpus;
+  int64_t r0, r1, d, slot_base;
+  const double *qt;   /* [nq8/8][d][8] transposed query blocks, zero padded */
+  const double *qn;   /* [nq] sqrt(normA) */
+  int64_t nq;
+  const uint8_t *live;
+  int use_threshold;
+  double min_score;
+  int64_t k;
+  hit_t *best;
+  int64_t *cnt;
+} vf_job_t;
+
+static void *vf_worker(void *arg) {
+  vf_job_t *j = (vf_job_t *)arg;
+  const int64_t d = j->d;
+  double *c = (double *)malloc(sizeof(double) * (size_t)(d > 0 ? d : 1));
+  for (int64_t b = 0; b < j->nq; b++) j->cnt[b] = 0;
+  for (int64_t r = j->r0; r < j->r1; r++) {
+    if (j->live && !j->live[r]) continue;
+    const uint16_t *row = j->corpus + r * d;
+    double nb = 0.0;
+    for (int64_t i = 0; i < d; i++) {
+      c[i] = bf16_to_f64(row[i]);
+      nb += c[i] * c[i];
+    }
+    const double sb = sqrt(nb);
+    for (int64_t b0 = 0; b0 < j->nq; b0 += 8) {
+      const double *qt = j->qt + (b0 / 8) * d * 8;
+      v2d a0 = {0.0, 0.0}, a1 = a0, a2 = a0, a3 = a0;
+      for (int64_t i = 0; i < d; i++) {
+        const v2d cv = {c[i], c[i]};
+        const v2d *q4 = (const v2d *)(qt + i * 8);
+        a0 = a0 + q4[0] * cv;
+        a1 = a1 + q4[1] * cv;
+        a2 = a2 + q4[2] * cv;
+        a3 = a3 + q4[3] * cv;
+      }
+      const double dots[8] = {a0[0], a0[1], a1[0], a1[1], a2[0], a2[1], a3[0], a3[1]};
+      for (int64_t e = 0; e < 8 && b0 + e < j->nq; e++) {
+        const int64_t b = b0 + e;
+        const double s = dots[e] / (j->qn[b] * sb);   /* embedder.ts:183 */
+        if (j->use_threshold ? (s >= j->min_score) : (s == s)) {
+          hit_t h = {s, r + j->slot_base};
+          j->cnt[b] = topk_insert(j->best + b * j->k, j->cnt[b], j->k, h);
+        }
+      }
+    }
+  }
+  free(c);
+  return NULL;
+}
+
+/* Same contract as rbk_oracle_search_batch_bf16_mt; slot_base is added to every returned slot. */
+int64_t rbk_oracle_search_batch_bf16_verify(const uint16_t *corpus, int64_t n, int64_t d, const double *queries,
+                                            int64_t nq, const uint8_t *live, int use_threshold, double min_score,
+                                            int64_t k_fetch, int n_threads, int64_t slot_base, int64_t *out_slots,
+                                            double *out_scores, int32_t *out_counts) {
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > n && n > 0) n_threads = (int)n;
+  const int64_t nblk = (nq + 7) / 8;
+  double *qt = (double *)aligned_alloc(64, sizeof(double) * (size_t)((nblk * d * 8 > 0 ? nblk * d * 8 : 8)));
+  double *qn = (double *)malloc(sizeof(double) * (size_t)(nq > 0 ? nq : 1));
+  memset(qt, 0, sizeof(double) * (size_t)(nblk * d * 8));
+  for (int64_t b = 0; b < nq; b++) {
+    double na = 0.0;
+    for (int64_t i = 0; i < d; i++) {
+      const double x = queries[b * d + i];
+      na += x * x;
+      qt[(b / 8) * d * 8 + i * 8 + (b % 8)] = x;
+    }
+    qn[b] = sqrt(na);
+  }
+  pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n_threads);
+  vf_job_t *jobs = (vf_job_t *)malloc(sizeof(vf_job_t) * (size_t)n_threads);
+  int64_t per = (n + n_threads - 1) / n_threads;
+  for (int t = 0; t < n_threads; t++) {
+    vf_job_t *j = &jobs[t];
+    j->corpus = corpus;
+    j->r0 = t * per < n ? t * per : n;
+    j->r1 = (t + 1) * per < n ? (t + 1) * per : n;
+    j->d = d;
+    j->slot_base = slot_base;
+    j->qt = qt;
+    j->qn = qn;
+    j->nq = nq;
+    j->live = live;
+    j->use_threshold = use_threshold;
+    j->min_score = min_score;
+    j->k = k_fetch;
+    j->best = (hit_t *)malloc(sizeof(hit_t) * (size_t)(nq * k_fetch > 0 ? nq * k_fetch : 1));
+    j->cnt = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nq > 0 ? nq : 1));
+    pthread_create(&th[t], NULL, vf_worker, j);
+  }
+  for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+  hit_t *best = (hit_t *)malloc(sizeof(hit_t) * (size_t)(k_fetch > 0 ? k_fetch : 1));
+  for (int64_t b = 0; b < nq; b++) {
+    int64_t cnt = 0;
+    for (int t = 0; t < n_threads; t++)
+      for (int64_t i = 0; i < jobs[t].cnt[b]; i++) cnt = topk_insert(best, cnt, k_fetch, jobs[t].best[b * k_fetch + i]);
+    for (int64_t i = 0; i < cnt; i++) {
+      out_slots[b * k_fetch + i] = best[i].slot;
+      out_scores[b * k_fetch + i] = best[i].score;
+    }
+    out_counts[b] = (int32_t)cnt;
+  }
+  free(best);
+  for (int t = 0; t < n_threads; t++) {
+    free(jobs[t].best);
+    free(jobs[t].cnt);
+  }
+  free(jobs);
+  free(th);
+  free(qt);
+  free(qn);
+  return 0;
+}
+
 /*
  * hybrid-search.ts:106-151 (S12).  Inputs are the chunk ids of the two ranked lists as
  * small integers (the caller interns the id strings).  score(id) = sum w/(k + i + 1),

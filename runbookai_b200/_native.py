@@ -21,7 +21,8 @@ SYMBOLS = [
     "rbk_index_set_slot_base", "rbk_index_append_f64", "rbk_index_append_f32", "rbk_index_append_bf16",
     "rbk_index_append_bf16_device", "rbk_index_overwrite_f64", "rbk_index_tombstone", "rbk_index_clear",
     "rbk_index_count", "rbk_index_size", "rbk_index_dim", "rbk_index_read_rows_bf16", "rbk_index_search_f64",
-    "rbk_index_search_f32", "rbk_index_search_device", "rbk_merge_topk_device", "rbk_packed_block_bytes",
+    "rbk_index_search_f32", "rbk_index_search_device", "rbk_index_search_device_async", "rbk_merge_topk_device",
+    "rbk_packed_block_bytes", "rbk_packed_flags_offset",
     "rbk_merge_topk_packed_device", "rbk_index_stats",
     "rbk_index_debug_scores_f32",
 ]
@@ -43,6 +44,7 @@ class RbkStats(C.Structure):
         ("scan_launches", C.c_int64), ("kernel_launches", C.c_int64), ("last_scan_ms", C.c_float),
         ("last_total_ms", C.c_float), ("last_kprime", C.c_int32), ("sm_count", C.c_int32),
         ("last_ring_stages", C.c_int32), ("retry_batches", C.c_int32),
+        ("scan_ms_total", C.c_double), ("scans_timed", C.c_int64),
     ]
 
 
@@ -76,10 +78,13 @@ def _load() -> C.CDLL:
     for n in ("rbk_index_search_f64", "rbk_index_search_f32"):
         getattr(lib, n).argtypes = [vp, vp, i32, i32, i32, f64, vp, vp, vp, C.POINTER(C.c_float)]
     lib.rbk_index_search_device.argtypes = [vp, vp, i32, i32, f64, vp, vp, vp]
+    lib.rbk_index_search_device_async.argtypes = [vp, vp, i32, i32, f64, vp, vp, vp, vp]
     lib.rbk_merge_topk_device.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.rbk_packed_block_bytes.argtypes = [i32, i32]
     lib.rbk_packed_block_bytes.restype = i64
-    lib.rbk_merge_topk_packed_device.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.rbk_packed_flags_offset.argtypes = [i32, i32]
+    lib.rbk_packed_flags_offset.restype = i64
+    lib.rbk_merge_topk_packed_device.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.rbk_index_stats.argtypes = [vp, C.POINTER(RbkStats)]
     lib.rbk_index_debug_scores_f32.argtypes = [vp, vp, i32, vp]
     return lib
@@ -206,6 +211,14 @@ class Index:
         check(lib.rbk_index_search_device(self._h, C.c_void_p(q_ptr), B, k_fetch, ms_arg, C.c_void_p(slots_ptr),
                                           C.c_void_p(scores_ptr), C.c_void_p(counts_ptr)))
 
+    def search_device_async(self, q_ptr: int, B: int, k_fetch: int, min_score: float | None, slots_ptr: int,
+                            scores_ptr: int, counts_ptr: int, flags_ptr: int) -> None:
+        """Enqueue only (no host sync); flags_ptr: device i32[B], 1 = answer not proven exact."""
+        ms_arg = -np.inf if min_score is None else float(min_score)
+        check(lib.rbk_index_search_device_async(self._h, C.c_void_p(q_ptr), B, k_fetch, ms_arg,
+                                                C.c_void_p(slots_ptr), C.c_void_p(scores_ptr),
+                                                C.c_void_p(counts_ptr), C.c_void_p(flags_ptr)))
+
     def debug_scores(self, queries_f32) -> np.ndarray:
         q = np.ascontiguousarray(queries_f32, dtype=np.float32)
         out = np.empty((q.shape[0], self.size()), dtype=np.float32)
@@ -229,8 +242,14 @@ def packed_block_bytes(B: int, k_fetch: int) -> int:
     return lib.rbk_packed_block_bytes(B, k_fetch)
 
 
+def packed_flags_offset(B: int, k_fetch: int) -> int:
+    return lib.rbk_packed_flags_offset(B, k_fetch)
+
+
 def merge_topk_packed_device(device: int, stream: int, G: int, B: int, k_fetch: int, blocks_ptr: int,
-                             out_slots_ptr: int, out_scores_ptr: int, out_counts_ptr: int) -> None:
+                             out_slots_ptr: int, out_scores_ptr: int, out_counts_ptr: int,
+                             out_flags_ptr: int | None = None) -> None:
+    """out_flags_ptr: device i32[B+1] ([b] = OR of the shards' exactness flags, [B] += dirty queries) or None."""
     check(lib.rbk_merge_topk_packed_device(device, C.c_void_p(stream), G, B, k_fetch, C.c_void_p(blocks_ptr),
                                            C.c_void_p(out_slots_ptr), C.c_void_p(out_scores_ptr),
-                                           C.c_void_p(out_counts_ptr)))
+                                           C.c_void_p(out_counts_ptr), C.c_void_p(out_flags_ptr or 0)))

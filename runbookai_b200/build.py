@@ -14,6 +14,8 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "lib" / "librbk_knn.so"
 SOURCES = ["rbk_capi.cu", "rbk_scan.cu", "rbk_scan2.cu", "rbk_scan3.cu", "rbk_ingest.cu", "rbk_finalize.cu"]
+# RBK_EXPERIMENTAL=1 in the environment of the BUILD adds -DRBK_EXPERIMENTAL: the measured-and-rejected kernel
+# variants of DESIGN.md §7 and their A/B switches (rbk_scan3.cu is empty without it).  Never set for a release.
 HEADERS = ["rbk_internal.h", "rbk_ptx.cuh", "rbk_epilogue.cuh", "../../include/rbk_knn.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -44,6 +46,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return LIB
     LIB.parent.mkdir(parents=True, exist_ok=True)
     cmd = [_nvcc(), *NVCC_FLAGS, *[str(CSRC / s) for s in SOURCES], "-o", str(LIB)]
+    if os.environ.get("RBK_EXPERIMENTAL") == "1":
+        cmd.insert(1, "-DRBK_EXPERIMENTAL")
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

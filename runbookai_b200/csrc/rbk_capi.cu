@@ -167,6 +167,12 @@ struct rbk_index {
   const void* tmap_c_base = nullptr;
   int64_t tmap_c_rows = -1;
   std::vector<cudaEvent_t> ev;
+  // scan-kernel timing without a host sync per search: (start, stop) event pairs are resolved lazily
+  // (rbk_index_stats, or when the ring wraps) into stats.scan_ms_total / stats.scans_timed
+  static constexpr int kTimingRing = 64;
+  cudaEvent_t tev[kTimingRing][2] = {};
+  uint64_t tev_head = 0, tev_tail = 0;   // [tail, head) pending
+  float pending_scan_ms = 0.f;           // scan time of the search being assembled (resolved pairs only)
   rbk_stats stats;
 };
 
@@ -190,6 +196,37 @@ cudaEvent_t get_event(rbk_index* ix, size_t i) {
     ix->ev.push_back(e);
   }
   return ix->ev[i];
+}
+
+// Fold finished (start, stop) pairs into the running totals.  wait = true: block on the pending ones.
+void resolve_scan_events(rbk_index* ix, bool wait) {
+  while (ix->tev_tail < ix->tev_head) {
+    cudaEvent_t* pr = ix->tev[ix->tev_tail % rbk_index::kTimingRing];
+    if (wait) cudaEventSynchronize(pr[1]);
+    else if (cudaEventQuery(pr[1]) != cudaSuccess) { cudaGetLastError(); break; }
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, pr[0], pr[1]) == cudaSuccess) {
+      ix->stats.scan_ms_total += t;
+      ix->stats.scans_timed++;
+      ix->stats.last_scan_ms = t;
+    }
+    ix->tev_tail++;
+  }
+}
+// Next (start, stop) pair of the ring; created on first use.
+cudaEvent_t* next_scan_events(rbk_index* ix) {
+  if (ix->tev_head - ix->tev_tail >= rbk_index::kTimingRing) {   // ring full: the oldest finished long ago
+    cudaEvent_t* old = ix->tev[ix->tev_tail % rbk_index::kTimingRing];
+    cudaEventSynchronize(old[1]);
+    resolve_scan_events(ix, false);
+  }
+  cudaEvent_t* pr = ix->tev[ix->tev_head % rbk_index::kTimingRing];
+  if (!pr[0]) {
+    cudaEventCreate(&pr[0]);
+    cudaEventCreate(&pr[1]);
+  }
+  ix->tev_head++;
+  return pr;
 }
 
 int64_t inv_norm_len(int64_t cap) { return round_up(cap, kBlockN) + kBlockN; }
@@ -303,12 +340,14 @@ rbk_status refresh_corpus_tmap(rbk_index* ix) {
   if (st != RBK_OK) return st;
   st = encode_rows_tmap(&ix->tmap_c_half, ix->rows, ix->n_rows, ix->dpad, kBlockN / 2);
   if (st != RBK_OK) return st;
+#ifdef RBK_EXPERIMENTAL
   st = encode_rows_tmap(&ix->tmap_c_half32, ix->rows, ix->n_rows, ix->dpad, kBlockN / 2, 32);
   if (st != RBK_OK) return st;
   st = encode_rows_tmap(&ix->tmap_c_pf, ix->rows, ix->n_rows, ix->dpad, kBlockN / 2, 256);
   if (st != RBK_OK) return st;
   st = encode_rows_tmap(&ix->tmap_c_r32, ix->rows, ix->n_rows, ix->dpad, scan3_box_rows());
   if (st != RBK_OK) return st;
+#endif
   ix->tmap_c_base = ix->rows;
   ix->tmap_c_rows = ix->n_rows;
   return RBK_OK;
@@ -344,8 +383,7 @@ QueryBuffers query_buffers(rbk_index* ix, int q0) {
 
 // Launch the scan (+ optionally finalize) for every sub-batch.  d_q: device queries.
 rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_fetch, double min_score,
-                    long long* d_slots, double* d_scores, int* d_counts, int* d_flags, float* dbg,
-                    size_t* ev_cursor) {
+                    long long* d_slots, double* d_scores, int* d_counts, int* d_flags, float* dbg) {
   const int kprime = pick_kprime(ix, k_fetch);
   ix->stats.last_kprime = kprime;
   CK(launch_prep_queries(d_q, src_type, B, ix->dim, ix->dpad, min_score,
@@ -402,12 +440,17 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
     sp.QB = QB;
     sp.R = R;
     sp.n_tiles = n_tiles;
-    CK(cudaEventRecord(get_event(ix, (*ev_cursor)++), ix->stream));
-    const bool resident = pairs && !ix->force_streamed && scan2_resident_fits(ix->dpad);
+    cudaEvent_t* tev = next_scan_events(ix);
+    CK(cudaEventRecord(tev[0], ix->stream));
     sp.prefetch_tiles = ix->prefetch_tiles;
     sp.perf_probe = ix->perf_probe;
     sp.max_lead_tiles = ix->max_lead_tiles;
+#ifdef RBK_EXPERIMENTAL
+    const bool resident = pairs && !ix->force_streamed && scan2_resident_fits(ix->dpad);
     const bool ts = pairs && ix->use_ts && scan3_fits(ix->dpad);
+#else
+    const bool resident = false, ts = false;
+#endif
     // lists per (unit, query): the default pair kernel splits every tile between two sets of epilogue warps
     // Eight epilogue warps (two lists per unit and query): measured in one box against four, +7-10 % at
     // B=256 up to 1M rows and +10-17 % at B=1024 up to 0.5M rows (where the filter is busy: thresholds still
@@ -422,6 +465,7 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
     // 0.07 ms at 65k rows): with one or two tiles per unit and only two seeds from each, a unit that reads the
     // histogram before ~k'/2 peers have seeded finds no threshold and floods its lists.
     sp.seed_tile = ix->seed_tile >= 0 ? ix->seed_tile : ((pairs && R * 2 * halves >= 4 * kprime) ? 1 : 0);
+#ifdef RBK_EXPERIMENTAL
     if (pairs && !ts && ix->hybrid_res_kb >= 0)
       CK(launch_scan2h(tmap_q, ix->tmap_c_half, sp, ix->hybrid_res_kb, ix->hybrid_slots, ix->stream));
     else if (ts)
@@ -430,7 +474,13 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
       CK(launch_scan2(tmap_q, (resident && scan2_resident_k() == 32) ? ix->tmap_c_half32 : ix->tmap_c_half,
                       ix->tmap_c_pf, sp, resident, halves, ix->stream, &ix->stats.last_ring_stages));
     else CK(launch_scan(tmap_q, ix->tmap_c, sp, ix->stream));
-    CK(cudaEventRecord(get_event(ix, (*ev_cursor)++), ix->stream));
+#else
+    if (pairs)
+      CK(launch_scan2(tmap_q, ix->tmap_c_half, ix->tmap_c_half, sp, false, halves, ix->stream,
+                      &ix->stats.last_ring_stages));
+    else CK(launch_scan(tmap_q, ix->tmap_c, sp, ix->stream));
+#endif
+    CK(cudaEventRecord(tev[1], ix->stream));
     ix->stats.scan_launches++;
     ix->stats.kernel_launches++;
     if (d_counts) {
@@ -502,22 +552,39 @@ rbk_status run_fallback(rbk_index* ix, const std::vector<int>& fails, int k_fetc
   return RBK_OK;
 }
 
-// Whole search.  q_host/q_dev: exactly one is non-null.  Host outputs (h_*) may be null
+rbk_status check_search_args(rbk_index* ix, int B, bool have_q, int query_dim, int k_fetch, double min_score) {
+  if (!ix) return fail(RBK_EINVAL, "null index");
+  if (B < 0 || (B > 0 && !have_q)) return fail(RBK_EINVAL, "bad queries argument");
+  if (k_fetch < 1 || k_fetch > RBK_MAX_K_FETCH) return fail(RBK_EINVAL, "k_fetch must be in [1, 112]");
+  if (query_dim != ix->dim) return fail(RBK_EDIM, "Vectors must have the same length");  // embedder.ts:170
+  if (min_score != min_score) return fail(RBK_EINVAL, "min_score is NaN");
+  return RBK_OK;
+}
+
+// Enqueue-only search of device-resident queries (caller holds the lock).  No host synchronisation: the
+// exactness flags land in d_flags and are the caller's to check (rbk_index_search_device_async).
+rbk_status enqueue_search(rbk_index* ix, const void* d_q, int src_type, int B, int k_fetch, double min_score,
+                          long long* d_slots, double* d_scores, int* d_counts, int* d_flags) {
+  ix->stats.searches++;
+  ix->stats.queries += B;
+  return run_scan(ix, d_q, src_type, B, k_fetch, min_score, d_slots, d_scores, d_counts, d_flags, nullptr);
+}
+
+// Whole search, synchronous.  q_host/q_dev: exactly one is non-null.  Host outputs (h_*) may be null
 // (device-output variant); device outputs may be null (host variant uses index scratch).
 rbk_status search_core(rbk_index* ix, const void* q_host, const void* q_dev, int elem, int B, int query_dim,
                        int k_fetch, double min_score, long long* d_slots, double* d_scores, int* d_counts,
                        int64_t* h_slots, double* h_scores, int32_t* h_counts, float* ms_out) {
-  if (!ix) return fail(RBK_EINVAL, "null index");
-  if (B < 0 || (B > 0 && !q_host && !q_dev)) return fail(RBK_EINVAL, "bad queries argument");
-  if (k_fetch < 1 || k_fetch > RBK_MAX_K_FETCH) return fail(RBK_EINVAL, "k_fetch must be in [1, 112]");
-  if (query_dim != ix->dim) return fail(RBK_EDIM, "Vectors must have the same length");  // embedder.ts:170
-  if (min_score != min_score) return fail(RBK_EINVAL, "min_score is NaN");
+  rbk_status st = check_search_args(ix, B, q_host || q_dev, query_dim, k_fetch, min_score);
+  if (st != RBK_OK) return st;
   std::lock_guard<std::mutex> lk(ix->mu);
   DeviceGuard dg(ix->device);
-  ix->stats.searches++;
   if (ms_out) *ms_out = 0.f;
-  if (B == 0) return RBK_OK;
-  rbk_status st = ensure_query_scratch(ix, B, elem);
+  if (B == 0) {
+    ix->stats.searches++;
+    return RBK_OK;
+  }
+  st = ensure_query_scratch(ix, B, elem);
   if (st != RBK_OK) return st;
   const size_t nout = static_cast<size_t>(B) * k_fetch;
   // Host-output calls use ONE packed device block (slots | scores | counts | flags) mirrored by one pinned
@@ -540,7 +607,8 @@ rbk_status search_core(rbk_index* ix, const void* q_host, const void* q_dev, int
     CK(ix->h_flags.ensure(B));
     h_flags = ix->h_flags.p;
   }
-  size_t evc = 2;
+  resolve_scan_events(ix, false);
+  const double scan_ms0 = ix->stats.scan_ms_total;
   CK(cudaEventRecord(get_event(ix, 0), ix->stream));
   const void* d_q = q_dev;
   if (q_host) {
@@ -548,8 +616,8 @@ rbk_status search_core(rbk_index* ix, const void* q_host, const void* q_dev, int
                        ix->stream));
     d_q = ix->q_raw.p;
   }
-  st = run_scan(ix, d_q, elem == 8 ? 0 : 1, B, k_fetch, min_score, d_slots, d_scores, d_counts, d_flags, nullptr,
-                &evc);
+  const int src_type = elem == 8 ? 0 : 1;
+  st = enqueue_search(ix, d_q, src_type, B, k_fetch, min_score, d_slots, d_scores, d_counts, d_flags);
   if (st != RBK_OK) return st;
   auto copy_back = [&]() -> cudaError_t {
     if (packed) return cudaMemcpyAsync(ix->h_block.p, ix->o_block.p, blk, cudaMemcpyDeviceToHost, ix->stream);
@@ -557,7 +625,7 @@ rbk_status search_core(rbk_index* ix, const void* q_host, const void* q_dev, int
   };
   CK(copy_back());
   CK(cudaEventRecord(get_event(ix, 1), ix->stream));
-  CK(cudaStreamSynchronize(ix->stream));
+  CK(cudaStreamSynchronize(ix->stream));   // the ONE host round trip of an exact batch
   std::vector<int> fails;
   for (int b = 0; b < B; ++b)
     if (h_flags[b]) fails.push_back(b);
@@ -568,8 +636,7 @@ rbk_status search_core(rbk_index* ix, const void* q_host, const void* q_dev, int
     // near-ties then fit among the candidates and the proof goes through.  Results of the queries that had
     // already passed are recomputed to the same values (both passes are exact).
     ix->kprime_override = kMaxKPrime;
-    st = run_scan(ix, d_q, elem == 8 ? 0 : 1, B, k_fetch, min_score, d_slots, d_scores, d_counts, d_flags, nullptr,
-                  &evc);
+    st = run_scan(ix, d_q, src_type, B, k_fetch, min_score, d_slots, d_scores, d_counts, d_flags, nullptr);
     ix->kprime_override = 0;
     if (st != RBK_OK) return st;
     CK(copy_back());
@@ -583,20 +650,17 @@ rbk_status search_core(rbk_index* ix, const void* q_host, const void* q_dev, int
   if (!fails.empty()) {
     st = run_fallback(ix, fails, k_fetch, min_score, d_slots, d_scores, d_counts);
     if (st != RBK_OK) return st;
+    // the exhaustive answers are exact by construction: clear the flags the caller may forward
+    CK(cudaMemsetAsync(d_flags, 0, sizeof(int) * B, ix->stream));
     if (packed) CK(copy_back());
     CK(cudaEventRecord(get_event(ix, 1), ix->stream));
     CK(cudaStreamSynchronize(ix->stream));
   }
-  float total = 0.f, scan = 0.f;
+  float total = 0.f;
   cudaEventElapsedTime(&total, get_event(ix, 0), get_event(ix, 1));
-  for (size_t i = 2; i + 1 < evc; i += 2) {
-    float t = 0.f;
-    cudaEventElapsedTime(&t, get_event(ix, i), get_event(ix, i + 1));
-    scan += t;
-  }
+  resolve_scan_events(ix, true);   // the stream is idle: every pair is final
   ix->stats.last_total_ms = total;
-  ix->stats.last_scan_ms = scan;
-  ix->stats.queries += B;
+  ix->stats.last_scan_ms = static_cast<float>(ix->stats.scan_ms_total - scan_ms0);
   if (ms_out) *ms_out = total;
   if (h_slots) {
     memcpy(h_slots, ix->h_block.p, sizeof(int64_t) * nout);
@@ -643,9 +707,10 @@ rbk_status rbk_index_create_ex(int32_t dim, int32_t device, int64_t capacity_hin
   ix->sm_count = prop.multiProcessorCount;
   memset(&ix->stats, 0, sizeof ix->stats);
   ix->stats.sm_count = ix->sm_count;
+#ifdef RBK_EXPERIMENTAL   // A/B switches of development builds; the shipped library reads no environment
   if (const char* m = getenv("RBK_KNN_MARGIN")) ix->margin = std::max(0, std::min(96, atoi(m)));
-  if (const char* m = getenv("RBK_KNN_FORCE_1CTA")) ix->force_1cta = atoi(m) != 0;   // A/B measurements only
-  if (const char* m = getenv("RBK_KNN_RESIDENT")) ix->force_streamed = atoi(m) == 0;   // experiments only
+  if (const char* m = getenv("RBK_KNN_FORCE_1CTA")) ix->force_1cta = atoi(m) != 0;
+  if (const char* m = getenv("RBK_KNN_RESIDENT")) ix->force_streamed = atoi(m) == 0;
   if (const char* m = getenv("RBK_KNN_TS")) ix->use_ts = atoi(m) != 0;
   if (const char* m = getenv("RBK_KNN_MAX_LEAD")) ix->max_lead_tiles = std::max(1, atoi(m));
   if (const char* m = getenv("RBK_KNN_SEED_TILE")) ix->seed_tile = atoi(m);
@@ -655,6 +720,7 @@ rbk_status rbk_index_create_ex(int32_t dim, int32_t device, int64_t capacity_hin
   if (const char* m = getenv("RBK_KNN_HYBRID_KB")) ix->hybrid_res_kb = atoi(m);
   if (const char* m = getenv("RBK_KNN_HYBRID_SLOTS")) ix->hybrid_slots = atoi(m);
   if (const char* m = getenv("RBK_KNN_PREFETCH_TILES")) ix->prefetch_tiles = std::max(0, std::min(64, atoi(m)));
+#endif
   e = cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     delete ix;
@@ -718,6 +784,9 @@ void rbk_index_destroy(rbk_index* ix) {
     ix->h_scores.release();
     ix->h_f32.release();
     for (cudaEvent_t e : ix->ev) cudaEventDestroy(e);
+    for (auto& pr : ix->tev)
+      for (cudaEvent_t e : pr)
+        if (e) cudaEventDestroy(e);
     if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
   }
   delete ix;
@@ -850,6 +919,23 @@ rbk_status rbk_index_search_device(rbk_index* ix, const void* dev_queries_f32, i
                      static_cast<int*>(dev_out_counts), nullptr, nullptr, nullptr, nullptr);
 }
 
+rbk_status rbk_index_search_device_async(rbk_index* ix, const void* dev_queries_f32, int32_t B, int32_t k_fetch,
+                                         double min_score, void* dev_out_slots, void* dev_out_scores,
+                                         void* dev_out_counts, void* dev_out_flags) {
+  if (B > 0 && (!dev_queries_f32 || !dev_out_slots || !dev_out_scores || !dev_out_counts || !dev_out_flags))
+    return fail(RBK_EINVAL, "null device pointer");
+  rbk_status st = check_search_args(ix, B, true, ix ? ix->dim : 0, k_fetch, min_score);
+  if (st != RBK_OK) return st;
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard dg(ix->device);
+  if (B == 0) return RBK_OK;
+  st = ensure_query_scratch(ix, B, 4);
+  if (st != RBK_OK) return st;
+  return enqueue_search(ix, dev_queries_f32, 1, B, k_fetch, min_score, static_cast<long long*>(dev_out_slots),
+                        static_cast<double*>(dev_out_scores), static_cast<int*>(dev_out_counts),
+                        static_cast<int*>(dev_out_flags));
+}
+
 rbk_status rbk_merge_topk_device(int32_t device, void* cuda_stream, int32_t G, int32_t B, int32_t k_fetch,
                                  const void* dev_slots, const void* dev_scores, const void* dev_counts,
                                  void* dev_out_slots, void* dev_out_scores, void* dev_out_counts) {
@@ -859,20 +945,25 @@ rbk_status rbk_merge_topk_device(int32_t device, void* cuda_stream, int32_t G, i
     return fail(RBK_EINVAL, "null device pointer");
   DeviceGuard dg(device);
   const size_t nk = static_cast<size_t>(B) * k_fetch;
-  CK(launch_merge_shards(G, B, k_fetch, dev_slots, dev_scores, dev_counts, nk * 8, nk * 8, static_cast<size_t>(B) * 4,
-                         static_cast<long long*>(dev_out_slots), static_cast<double*>(dev_out_scores),
-                         static_cast<int*>(dev_out_counts), static_cast<cudaStream_t>(cuda_stream)));
+  CK(launch_merge_shards(G, B, k_fetch, dev_slots, dev_scores, dev_counts, nullptr, nk * 8, nk * 8,
+                         static_cast<size_t>(B) * 4, 0, static_cast<long long*>(dev_out_slots),
+                         static_cast<double*>(dev_out_scores), static_cast<int*>(dev_out_counts), nullptr,
+                         static_cast<cudaStream_t>(cuda_stream)));
   return RBK_OK;
 }
 
 int64_t rbk_packed_block_bytes(int32_t B, int32_t k_fetch) {
+  const int64_t nk = static_cast<int64_t>(B) * k_fetch;
+  return nk * 16 + 2 * (((static_cast<int64_t>(B) * 4 + 15) / 16) * 16);   // slots | scores | counts | flags
+}
+int64_t rbk_packed_flags_offset(int32_t B, int32_t k_fetch) {
   const int64_t nk = static_cast<int64_t>(B) * k_fetch;
   return nk * 16 + ((static_cast<int64_t>(B) * 4 + 15) / 16) * 16;
 }
 
 rbk_status rbk_merge_topk_packed_device(int32_t device, void* cuda_stream, int32_t G, int32_t B, int32_t k_fetch,
                                         const void* dev_blocks, void* dev_out_slots, void* dev_out_scores,
-                                        void* dev_out_counts) {
+                                        void* dev_out_counts, void* dev_out_flags) {
   if (G < 1 || B < 0 || k_fetch < 1) return fail(RBK_EINVAL, "bad merge shape");
   if (B == 0) return RBK_OK;
   if (!dev_blocks || !dev_out_slots || !dev_out_scores || !dev_out_counts)
@@ -881,14 +972,19 @@ rbk_status rbk_merge_topk_packed_device(int32_t device, void* cuda_stream, int32
   const size_t nk = static_cast<size_t>(B) * k_fetch;
   const size_t stride = static_cast<size_t>(rbk_packed_block_bytes(B, k_fetch));
   const char* base = static_cast<const char*>(dev_blocks);
-  CK(launch_merge_shards(G, B, k_fetch, base, base + nk * 8, base + nk * 16, stride, stride, stride,
-                         static_cast<long long*>(dev_out_slots), static_cast<double*>(dev_out_scores),
-                         static_cast<int*>(dev_out_counts), static_cast<cudaStream_t>(cuda_stream)));
+  CK(launch_merge_shards(G, B, k_fetch, base, base + nk * 8, base + nk * 16,
+                         dev_out_flags ? base + rbk_packed_flags_offset(B, k_fetch) : nullptr, stride, stride, stride,
+                         stride, static_cast<long long*>(dev_out_slots), static_cast<double*>(dev_out_scores),
+                         static_cast<int*>(dev_out_counts), static_cast<int*>(dev_out_flags),
+                         static_cast<cudaStream_t>(cuda_stream)));
   return RBK_OK;
 }
 
-rbk_status rbk_index_stats(const rbk_index* ix, rbk_stats* out) {
+rbk_status rbk_index_stats(rbk_index* ix, rbk_stats* out) {
   if (!ix || !out) return fail(RBK_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard dg(ix->device);
+  resolve_scan_events(ix, false);   // fold in every scan that has finished; never blocks
   *out = ix->stats;
   return RBK_OK;
 }
@@ -904,8 +1000,7 @@ rbk_status rbk_index_debug_scores_f32(rbk_index* ix, const float* queries, int32
   CK(ix->dbg.ensure(n));
   CK(cudaMemsetAsync(ix->dbg.p, 0xFF, n * 4, ix->stream));
   CK(cudaMemcpyAsync(ix->q_raw.p, queries, static_cast<size_t>(B) * ix->dim * 4, cudaMemcpyHostToDevice, ix->stream));
-  size_t evc = 2;
-  st = run_scan(ix, ix->q_raw.p, 1, B, 16, -INFINITY, nullptr, nullptr, nullptr, nullptr, ix->dbg.p, &evc);
+  st = run_scan(ix, ix->q_raw.p, 1, B, 16, -INFINITY, nullptr, nullptr, nullptr, nullptr, ix->dbg.p);
   if (st != RBK_OK) return st;
   std::vector<float> invq(B);
   CK(cudaMemcpyAsync(out_scores, ix->dbg.p, n * 4, cudaMemcpyDeviceToHost, ix->stream));

@@ -65,7 +65,7 @@ __device__ __forceinline__ void filter_init(FilterState& s, bool valid, float th
 // Bins are fetched 16 at a time (four independent 16-byte L2 loads in flight): a dependent chain
 // of single loads cost ~0.7 us per 4 bins and made this function 23 % of the epilogue's time.
 static __device__ __noinline__ bool filter_refresh(FilterState& s, int kprime) {
-  if (!s.valid || s.probe == 3) return false;
+  if (!s.valid || (kExperimental && s.probe == 3)) return false;
   const int mb = __ldcg(s.maxbin_q);
   if (mb <= s.tb) return false;
   const uint4* h4 = reinterpret_cast<const uint4*>(s.hist_q);
@@ -148,7 +148,7 @@ __device__ __forceinline__ void hist_add(FilterState& s, float t) {
 __device__ __forceinline__ void filter_append(FilterState& s, float t, uint32_t row) {
   s.list[s.cnt] = pack_key(t, row);
   ++s.cnt;
-  if (s.nohist || s.probe == 3) return;
+  if (s.nohist || (kExperimental && s.probe == 3)) return;
   hist_add(s, t);
 }
 
@@ -206,7 +206,7 @@ __device__ __forceinline__ void filter_chunk(FilterState& s, const uint32_t (&v)
     g[j] = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));   // fmaxf drops NaN (dead / out-of-range rows)
     m = fmaxf(m, g[j]);
   }
-  if (s.probe == 2) {   // probe: fast path only
+  if (kExperimental && s.probe == 2) {   // probe: fast path only
     if (m == 12345.678f) s.cnt = 1;
     return;
   }
@@ -344,7 +344,7 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
   filter_init(fs, q_valid, q_valid ? p.thr_init[q] : INFINITY, q_valid ? p.inv_norm_q[q] : 0.f,
               p.cand + list_id * static_cast<size_t>(kListCap),
               p.hist + static_cast<size_t>(q_valid ? q : 0) * kHistBins, p.maxbin + (q_valid ? q : 0));
-  fs.probe = p.perf_probe;
+  fs.probe = kExperimental ? p.perf_probe : 0;
 #ifdef RBK_EPI_PROFILE   // cycle breakdown of one epilogue thread per CTA (development builds only)
   long long c_wait = 0, c_chunk = 0, c_compact = 0, c_pub = 0, c_bar = 0, c_seed = 0;
   long long c_tile[4] = {0, 0, 0, 0}, c_sub[4] = {0, 0, 0, 0};
@@ -409,7 +409,7 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
     const uint32_t tcol =
         tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * kBlockN + col0);
     auto process = [&](uint32_t (&v)[32], int chunk) {
-      if (p.perf_probe == 1) {   // timing probe: keep the TMEM traffic, drop the arithmetic
+      if (kExperimental && p.perf_probe == 1) {   // timing probe: keep the TMEM traffic, drop the arithmetic
         if (v[0] == 0x7FC12345u) fs.cnt = 1;
         return;
       }
@@ -425,7 +425,7 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
       }
     };
     uint32_t va[32], vb[32];
-    if (it == 0 && p.perf_probe == 0) {
+    if (it == 0 && (!kExperimental || p.perf_probe == 0)) {
       // seeding pass (see seed_chunk): count the best rows of this tile, then take the threshold they give
 #ifdef RBK_EPI_PROFILE
       const long long t_seed = clock64();

@@ -594,9 +594,11 @@ __global__ void __launch_bounds__(kExThreads) exact_merge_kernel(ExactParams p) 
 // entries of that list that come before it (binary search).
 __global__ void __launch_bounds__(128) merge_shards_kernel(int G, int B, int k, const char* __restrict__ slots_base,
                                                            const char* __restrict__ scores_base,
-                                                           const char* __restrict__ counts_base, size_t slots_stride,
+                                                           const char* __restrict__ counts_base,
+                                                           const char* __restrict__ flags_base, size_t slots_stride,
                                                            size_t scores_stride, size_t counts_stride,
-                                                           long long* out_slots, double* out_scores, int* out_counts) {
+                                                           size_t flags_stride, long long* out_slots,
+                                                           double* out_scores, int* out_counts, int* out_flags) {
   // shard g's arrays start g * stride bytes after shard 0's (dense [G][...] arrays: stride = array size;
   // packed per-rank blocks, e.g. straight out of ONE all-gather: the same block stride for all three)
   auto slots_of = [&](int g) { return reinterpret_cast<const long long*>(slots_base + g * slots_stride); };
@@ -636,7 +638,17 @@ __global__ void __launch_bounds__(128) merge_shards_kernel(int G, int B, int k, 
     out_slots[static_cast<size_t>(b) * k + i] = -1;
     out_scores[static_cast<size_t>(b) * k + i] = __longlong_as_double(0x7FF8000000000000ll);
   }
-  if (threadIdx.x == 0) out_counts[b] = n_out;
+  if (threadIdx.x == 0) {
+    out_counts[b] = n_out;
+    if (out_flags != nullptr) {
+      // "not provably exact" travels with the lists: a query is dirty if any shard's proof failed.  out_flags[B]
+      // counts dirty queries across calls (the caller zeroes it), so a pipelined caller can check once at the end.
+      int dirty = 0;
+      for (int g = 0; g < G; ++g) dirty |= reinterpret_cast<const int*>(flags_base + g * flags_stride)[b];
+      out_flags[b] = dirty;
+      if (dirty) atomicAdd(out_flags + B, 1);
+    }
+  }
 }
 
 }  // namespace
@@ -675,13 +687,15 @@ cudaError_t launch_exact_fallback(const ExactParams& p, cudaStream_t stream) {
 }
 
 cudaError_t launch_merge_shards(int G, int B, int k_fetch, const void* slots, const void* scores, const void* counts,
-                                size_t slots_stride, size_t scores_stride, size_t counts_stride, long long* out_slots,
-                                double* out_scores, int* out_counts, cudaStream_t stream) {
+                                const void* flags, size_t slots_stride, size_t scores_stride, size_t counts_stride,
+                                size_t flags_stride, long long* out_slots, double* out_scores, int* out_counts,
+                                int* out_flags, cudaStream_t stream) {
   if (B <= 0) return cudaSuccess;
   merge_shards_kernel<<<B, 128, 0, stream>>>(G, B, k_fetch, static_cast<const char*>(slots),
                                              static_cast<const char*>(scores), static_cast<const char*>(counts),
-                                             slots_stride, scores_stride, counts_stride, out_slots, out_scores,
-                                             out_counts);
+                                             static_cast<const char*>(flags), slots_stride, scores_stride,
+                                             counts_stride, flags_stride, out_slots, out_scores, out_counts,
+                                             flags ? out_flags : nullptr);
   return cudaGetLastError();
 }
 

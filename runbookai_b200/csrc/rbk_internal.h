@@ -21,6 +21,15 @@ constexpr int kMaxLeadTiles = 4;    // lockstep: max tiles a CTA may lead the sl
                                     // under the power cap: 8 -> 74.2 k, 4 -> 76.4 k, 2 -> 77.4 k q/s; short kernels: 8 best by 2 %)
 constexpr int kHistBins = 1024;     // per-query score histogram, cosine in [-1,1] -> bin width 1/512
 
+// The default build ships ONE scan path per batch size (scan_kernel for B <= 128, the streamed CTA-pair kernel
+// above).  -DRBK_EXPERIMENTAL additionally compiles the measured-and-rejected variants of DESIGN.md §7 (query-
+// resident / hybrid / TMEM-query pair kernels, the timing probes) and the environment switches that select them.
+#ifdef RBK_EXPERIMENTAL
+constexpr bool kExperimental = true;
+#else
+constexpr bool kExperimental = false;
+#endif
+
 struct ScanParams {
   const float* inv_norm_c;  // [rows padded to kBlockN], NaN = dead / out of range
   const float* thr_init;    // [B] initial threshold, raw domain (acc * inv_norm_c); -inf = none
@@ -135,10 +144,12 @@ struct ExactParams {
 };
 cudaError_t launch_exact_fallback(const ExactParams& p, cudaStream_t stream);
 
-// slots/scores/counts point at shard 0's arrays; shard g's arrays start g * <stride> bytes later.
+// slots/scores/counts/flags point at shard 0's arrays; shard g's arrays start g * <stride> bytes later.
+// flags (nullable): per-shard exactness flags i32[B]; out_flags: i32[B+1] ([b] = OR over shards, [B] += dirty queries).
 cudaError_t launch_merge_shards(int G, int B, int k_fetch, const void* slots, const void* scores, const void* counts,
-                                size_t slots_stride, size_t scores_stride, size_t counts_stride, long long* out_slots,
-                                double* out_scores, int* out_counts, cudaStream_t stream);
+                                const void* flags, size_t slots_stride, size_t scores_stride, size_t counts_stride,
+                                size_t flags_stride, long long* out_slots, double* out_scores, int* out_counts,
+                                int* out_flags, cudaStream_t stream);
 
 // Bound on the fp32 tensor-core accumulation + scaling error of an approximate cosine.
 inline double accumulation_eps(int d) { return (double)(d + 8) * (1.0 / 4194304.0); }  // (d+8) * 2^-22

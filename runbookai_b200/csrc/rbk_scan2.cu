@@ -270,6 +270,7 @@ bool smem_base_is_aligned() {
   return cached[dev] == 1;
 }
 
+#ifdef RBK_EXPERIMENTAL
 // ---------------------------------------------------------------------------------------------
 // Hybrid variant: the first `res_kb` 64-column panels of the CTA's queries stay resident in smem,
 // the rest of the query slab and the whole corpus stream through a ring of 16 KB SLOTS (a k-block
@@ -426,6 +427,8 @@ scan2h_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   }
 }
 
+#endif  // RBK_EXPERIMENTAL
+
 }  // namespace
 
 // Can the query block stay resident for this padded dim?
@@ -452,22 +455,31 @@ static cudaError_t launch_scan2_t(const CUtensorMap& tmap_q, const CUtensorMap& 
 // halves: 1 = four epilogue warps per CTA, 2 = eight (two lists per unit and query; see run_epilogue).
 cudaError_t launch_scan2(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const CUtensorMap& tmap_pf,
                          const ScanParams& p, bool resident, int halves, cudaStream_t stream, int* ring_stages_out) {
+#ifdef RBK_EXPERIMENTAL
   if (resident) {
     const size_t smem = static_cast<size_t>(p.num_kb) * kPanelBytes + static_cast<size_t>(kStagesR) * kStageRBytes +
                         sizeof(SmemTail2);
     return halves == 2 ? launch_scan2_t<true, 2>(tmap_q, tmap_c, tmap_pf, p, smem, kStagesS, stream)
                        : launch_scan2_t<true, 1>(tmap_q, tmap_c, tmap_pf, p, smem, kStagesS, stream);
   }
+#else
+  if (resident) return cudaErrorNotSupported;
+#endif
   // 7 stages fill the 227 KB exactly (no alignment slack): only when the dynamic smem base is 1024-aligned on
   // this device/driver (probed once); otherwise 6 stages + 1 KB of slack
   const int n_stages = smem_base_is_aligned() ? kStagesS : kStagesS - 1;
   size_t smem = static_cast<size_t>(n_stages) * kStageSBytes + sizeof(SmemTail2);
   if (smem + 1024 <= kMaxSmem) smem += 1024;
   if (ring_stages_out) *ring_stages_out = n_stages;
-  return halves == 2 ? launch_scan2_t<false, 2>(tmap_q, tmap_c, tmap_pf, p, smem, n_stages, stream)
-                     : launch_scan2_t<false, 1>(tmap_q, tmap_c, tmap_pf, p, smem, n_stages, stream);
+#ifdef RBK_EXPERIMENTAL
+  if (halves != 2) return launch_scan2_t<false, 1>(tmap_q, tmap_c, tmap_pf, p, smem, n_stages, stream);
+#else
+  if (halves != 2) return cudaErrorNotSupported;   // the shipped kernel always runs eight epilogue warps
+#endif
+  return launch_scan2_t<false, 2>(tmap_q, tmap_c, tmap_pf, p, smem, n_stages, stream);
 }
 
+#ifdef RBK_EXPERIMENTAL
 // Hybrid launch: res_kb resident query panels + n_slots ring slots (16 KB each) must fit 227 KB.
 cudaError_t launch_scan2h(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c_half, const ScanParams& p, int res_kb,
                           int n_slots, cudaStream_t stream) {
@@ -481,5 +493,7 @@ cudaError_t launch_scan2h(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c_h
   scan2h_kernel<<<2 * p.QB * p.R, kScanThreads, smem, stream>>>(tmap_q, tmap_c_half, p, res_kb, n_slots);
   return cudaGetLastError();
 }
+
+#endif  // RBK_EXPERIMENTAL
 
 }  // namespace rbk

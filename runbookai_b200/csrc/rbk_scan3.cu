@@ -17,6 +17,7 @@
 //
 // The pair protocol (leader-only arrive.expect_tx, multicast commits, remote tmem_empty
 // arrive) is the one of rbk_scan2.cu.
+#ifdef RBK_EXPERIMENTAL   // measured and rejected: not part of the default build
 #include "rbk_epilogue.cuh"
 #include "rbk_internal.h"
 #include "rbk_ptx.cuh"
@@ -301,3 +302,5 @@ cudaError_t launch_scan3(const CUtensorMap& tmap_c, const ScanParams& p, const u
 }
 
 }  // namespace rbk
+
+#endif  // RBK_EXPERIMENTAL

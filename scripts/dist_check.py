@@ -30,14 +30,15 @@ def main():
         corpus[g * per + 1] = corpus[g * per - 2]
     q = synth.random_queries(b, d, 6)
     synth.plant_neighbours(corpus, q, 8, 7)
+    # 150 exact duplicates of one row, all in shard 0: more ties than any candidate margin holds -> that shard's
+    # proof fails for query 0, the dirty flag travels through the all-gather and EVERY rank re-answers the batch
+    dup = np.random.default_rng(8).choice(per - 10, 150, replace=False)
+    corpus[dup] = synth.f32_to_bf16_bits(q[0] * 0.5)
     lo, hi = shard_bounds(n, world, rank)
     ix = Index(d, device=local, capacity_hint=hi - lo)
     ix.set_slot_base(lo)
     ix.append_bf16(corpus[lo:hi])
-    stream = torch.cuda.Stream(dev)
-    torch.cuda.set_stream(stream)
-    ix.set_stream(stream.cuda_stream)
-    sh = ShardedSearcher(ix)
+    sh = ShardedSearcher(ix)               # one stream for the engine, NCCL and the copies
     ok = True
     for ms in (None, 0.5):
         s, v, c = sh.search(torch.from_numpy(q), k, ms, dev)
@@ -45,12 +46,14 @@ def main():
         if rank == 0:
             import oracle
             nq = 64
-            es, ev, ec = oracle.search_batch_mt(corpus, q[:nq].astype(np.float64), k, ms)
+            es, ev, ec = oracle.search_batch_verify(corpus, q[:nq].astype(np.float64), k, ms)
             good = (c[:nq] == ec).all() and all(
                 (s[i, :ec[i]] == es[i, :ec[i]]).all() and (v[i, :ec[i]] == ev[i, :ec[i]]).all() for i in range(nq))
             ok = ok and bool(good)
             print(json.dumps({"world": world, "min_score": ms, "parity": bool(good), "counts": c[:4].tolist(),
-                              "fallback": ix.stats()["fallback_queries"]}), flush=True)
+                              "fallback": ix.stats()["fallback_queries"], "redone_batches": sh.redone_batches}),
+                  flush=True)
+            ok = ok and sh.redone_batches >= 1     # the dirty-flag path was really taken
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.barrier()

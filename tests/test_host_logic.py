@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol(native):
     lib = ctypes.CDLL(str(native.LIB_PATH))
     for sym in sorted(declared):
         assert hasattr(lib, sym), sym
-    assert lib.rbk_abi_version() == 1
+    assert lib.rbk_abi_version() == 2
 
 
 @pytest.mark.skipif(HAS_CUDA, reason="checks the no-GPU failure mode")

@@ -86,6 +86,32 @@ def test_multithreaded_select_equals_full_stable_sort(oracle_mod):
             assert S[b, :C[b]].tolist() == s.tolist() and V[b, :C[b]].tolist() == v.tolist()
 
 
+def test_verify_variant_is_bit_identical_to_the_literal_loop(oracle_mod):
+    """rbk_oracle_search_batch_bf16_verify (norms hoisted, 8 queries' dot chains side by side) is the checker of
+    the large GPU runs: it must return exactly what the literal per-pair loop returns - slots, fp64 scores,
+    counts - including ties, NaN rows, tombstones, a threshold, ragged query counts and chunked use."""
+    from runbookai_b200 import synth
+    for n, d, nq, k, ms in ((4000, 768, 19, 32, None), (3000, 100, 3, 8, 0.05), (900, 1536, 64, 16, None),
+                            (500, 7, 9, 5, 0.2), (50, 33, 1, 112, None)):
+        c = synth.random_corpus(n, d, 50 + n)
+        c[5] = 0
+        c[17] = c[3]
+        c[n - 1] = c[3]
+        q = synth.random_queries(nq, d, 60 + d).astype(np.float64)
+        if nq > 2:
+            q[2] = 0.0                                   # zero query: NaN everywhere
+        live = np.ones(n, dtype=np.uint8)
+        live[::7] = 0
+        for lv in (None, live):
+            a = oracle_mod.search_batch_mt(c, q, k, ms, live=lv, n_threads=3)
+            b = oracle_mod.search_batch_verify(c, q, k, ms, live=lv, n_threads=5)
+            assert (a[0] == b[0]).all() and np.array_equal(a[1], b[1], equal_nan=True) and (a[2] == b[2]).all()
+            cc = oracle_mod.search_chunked(lambda r0, m: c[r0:r0 + m], n, q, k, ms, chunk_rows=333, live=lv,
+                                           slot_base=1000)
+            assert (np.where(a[0] >= 0, a[0] + 1000, -1) == cc[0]).all()
+            assert np.array_equal(a[1], cc[1], equal_nan=True) and (a[2] == cc[2]).all()
+
+
 def test_bf16_corpus_path_equals_f64_path(oracle_mod):
     from runbookai_b200 import synth
     c = synth.random_corpus(500, 33, 7)
