@@ -225,13 +225,16 @@ def oracle_parity(ctx, ix, lo, hi, q_host_np, k_fetch, min_score, got, budget_s=
     chunk = 1 << 19
     t0 = time.perf_counter()
     parts = []
-    for r0 in range(0, n_local, chunk):
-        m = min(chunk, n_local - r0)
-        rows = ix.read_rows_bf16(r0, m)
-        parts.append(oracle.search_batch_verify(rows, q, k_fetch, min_score, n_threads=threads, slot_base=lo + r0))
-        if r0 == 0 and n_local > chunk:
+    for i, r0 in enumerate(range(0, max(n_local, 1), chunk)):
+        m = max(0, min(chunk, n_local - r0))
+        if m > 0:
+            rows = ix.read_rows_bf16(r0, m)
+            parts.append(oracle.search_batch_verify(rows, q, k_fetch, min_score, n_threads=threads,
+                                                    slot_base=lo + r0))
+        if i == 0:
             # keep the default run inside a few minutes on a slow / shared host: fewer queries, never fewer rows
-            proj = (time.perf_counter() - t0) * (n_local / m)
+            # (every rank takes part in the decision, also one whose shard is empty)
+            proj = (time.perf_counter() - t0) * (n_local / m) if m > 0 else 0.0
             nq_new = nq
             while proj * nq_new / nq > budget_s and nq_new > 8:
                 nq_new //= 2

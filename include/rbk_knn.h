@@ -87,8 +87,17 @@ rbk_status rbk_index_append_bf16(rbk_index* idx, const uint16_t* rows, int64_t n
 /* Same, rows already in device memory on the index's GPU (bulk load without a PCIe hop). */
 rbk_status rbk_index_append_bf16_device(rbk_index* idx, const void* dev_rows, int64_t n_rows,
                                         int64_t* first_slot_out);
+/* f64 rows (the BLOB layout) already on the device, e.g. a sidecar file read with GPUDirect or staged by the host
+ * framework in large pinned chunks. */
+rbk_status rbk_index_append_f64_device(rbk_index* idx, const void* dev_rows, int64_t n_rows, int64_t* first_slot_out);
 /* `this.embeddings.set(id, e)` on an existing id keeps its Map position (S9b). */
 rbk_status rbk_index_overwrite_f64(rbk_index* idx, int64_t local_slot, const double* row);
+/* The same for n rows at once - a re-embedded document (addChunks over existing ids, vector-store.ts:135-183):
+ * rows[i] (n x dim, f64) replaces local_slots[i].  One call, one host round trip for the whole batch.  A slot that
+ * is tombstoned stays dead and makes the call return RBK_EINVAL after the LIVE slots of the batch have been
+ * written (the host mirror never overwrites a deleted id, so this is a caller bug, not a data path).  local_slots
+ * must be distinct (the host mirror keeps the last value per id). */
+rbk_status rbk_index_overwrite_f64_batch(rbk_index* idx, const int64_t* local_slots, int64_t n, const double* rows);
 /* `this.embeddings.delete(id)`: the rows stop matching; slots are not reused. */
 rbk_status rbk_index_tombstone(rbk_index* idx, const int64_t* local_slots, int64_t n);
 rbk_status rbk_index_clear(rbk_index* idx);

@@ -19,7 +19,7 @@ RBK_MAX_K_FETCH = 112
 SYMBOLS = [
     "rbk_abi_version", "rbk_last_error", "rbk_index_create", "rbk_index_create_ex", "rbk_index_destroy", "rbk_index_set_stream",
     "rbk_index_set_slot_base", "rbk_index_append_f64", "rbk_index_append_f32", "rbk_index_append_bf16",
-    "rbk_index_append_bf16_device", "rbk_index_overwrite_f64", "rbk_index_tombstone", "rbk_index_clear",
+    "rbk_index_append_bf16_device", "rbk_index_append_f64_device", "rbk_index_overwrite_f64", "rbk_index_overwrite_f64_batch", "rbk_index_tombstone", "rbk_index_clear",
     "rbk_index_count", "rbk_index_size", "rbk_index_dim", "rbk_index_read_rows_bf16", "rbk_index_search_f64",
     "rbk_index_search_f32", "rbk_index_search_device", "rbk_index_search_device_async", "rbk_merge_topk_device",
     "rbk_packed_block_bytes", "rbk_packed_flags_offset",
@@ -64,9 +64,10 @@ def _load() -> C.CDLL:
     lib.rbk_index_set_stream.argtypes = [vp, vp]
     lib.rbk_index_set_slot_base.argtypes = [vp, i64]
     for n in ("rbk_index_append_f64", "rbk_index_append_f32", "rbk_index_append_bf16",
-              "rbk_index_append_bf16_device"):
+              "rbk_index_append_bf16_device", "rbk_index_append_f64_device"):
         getattr(lib, n).argtypes = [vp, vp, i64, C.POINTER(i64)]
     lib.rbk_index_overwrite_f64.argtypes = [vp, i64, vp]
+    lib.rbk_index_overwrite_f64_batch.argtypes = [vp, vp, i64, vp]
     lib.rbk_index_tombstone.argtypes = [vp, vp, i64]
     lib.rbk_index_clear.argtypes = [vp]
     for n in ("rbk_index_count", "rbk_index_size"):
@@ -160,11 +161,24 @@ class Index:
         check(lib.rbk_index_append_bf16_device(self._h, C.c_void_p(dev_ptr), n_rows, C.byref(first)))
         return first.value
 
+    def append_f64_device(self, dev_ptr: int, n_rows: int) -> int:
+        first = C.c_int64(-1)
+        check(lib.rbk_index_append_f64_device(self._h, C.c_void_p(dev_ptr), n_rows, C.byref(first)))
+        return first.value
+
     def overwrite_f64(self, slot: int, row) -> None:
         r = np.ascontiguousarray(row, dtype=np.float64)
         if r.shape != (self.dim,):
             raise DimensionError(RBK_EDIM, "Vectors must have the same length")
         check(lib.rbk_index_overwrite_f64(self._h, slot, ptr(r)))
+
+    def overwrite_f64_batch(self, slots, rows) -> None:
+        """rows[i] replaces slots[i]; one call and one host round trip for the whole batch."""
+        s = np.ascontiguousarray(slots, dtype=np.int64)
+        r = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, self.dim) if len(s) else np.zeros((0, self.dim))
+        if r.shape != (s.shape[0], self.dim):
+            raise DimensionError(RBK_EDIM, "Vectors must have the same length")
+        check(lib.rbk_index_overwrite_f64_batch(self._h, ptr(s), s.shape[0], ptr(r)))
 
     def tombstone(self, slots) -> None:
         s = np.ascontiguousarray(slots, dtype=np.int64)

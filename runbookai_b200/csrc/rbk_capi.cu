@@ -319,10 +319,13 @@ rbk_status append_rows(rbk_index* ix, const void* src, bool is_device, int elem,
       // synchronous with respect to the host buffer, the kernel is ordered by the stream
     }
   }
-  CK(launch_row_norms(dst0, dst64, n, ix->dim, ix->dpad, ix->inv_norm + ix->n_rows, ix->norm2 + ix->n_rows,
-                      ix->d_counter + 1, ix->stream));
-  ix->stats.kernel_launches++;
-  CK(cudaStreamSynchronize(ix->stream));
+  CK(launch_row_norms(ix->rows, ix->keep_f64 ? ix->rows_f64 : nullptr, ix->n_rows, n, ix->dim, ix->dpad, ix->inv_norm,
+                      ix->norm2, ix->d_counter + 1, ix->stream));
+  ix->stats.kernel_launches += ix->keep_f64 ? 2 : 1;
+  // Host sources: pageable H2D copies have consumed the caller's buffer when cudaMemcpyAsync returns and everything
+  // after is stream-ordered, so an append costs no host round trip.  Device sources are read by the copy/convert
+  // kernel itself: the caller may free them as soon as we return, so wait for that.
+  if (is_device) CK(cudaStreamSynchronize(ix->stream));
   ix->n_rows += n;
   ix->n_live += n;
   return RBK_OK;
@@ -821,28 +824,51 @@ rbk_status rbk_index_append_bf16(rbk_index* ix, const uint16_t* rows, int64_t n,
 rbk_status rbk_index_append_bf16_device(rbk_index* ix, const void* dev_rows, int64_t n, int64_t* first) {
   return append_rows(ix, dev_rows, true, 2, n, first);
 }
+rbk_status rbk_index_append_f64_device(rbk_index* ix, const void* dev_rows, int64_t n, int64_t* first) {
+  return append_rows(ix, dev_rows, true, 8, n, first);
+}
 
-rbk_status rbk_index_overwrite_f64(rbk_index* ix, int64_t slot, const double* row) {
-  if (!ix || !row) return fail(RBK_EINVAL, "null argument");
+rbk_status rbk_index_overwrite_f64_batch(rbk_index* ix, const int64_t* slots, int64_t n, const double* rows) {
+  if (!ix) return fail(RBK_EINVAL, "null index");
+  if (n < 0 || (n > 0 && (!slots || !rows))) return fail(RBK_EINVAL, "bad argument");
+  if (n == 0) return RBK_OK;
   std::lock_guard<std::mutex> lk(ix->mu);
   DeviceGuard dg(ix->device);
-  if (slot < 0 || slot >= ix->n_rows) return fail(RBK_EINVAL, "slot out of range");
-  // a tombstoned slot stays dead: the host never overwrites a deleted id (S9b), and the
-  // norm kernel would otherwise revive it
-  unsigned int word = 0;
-  CK(cudaMemcpyAsync(&word, ix->dead_bits + (slot >> 5), 4, cudaMemcpyDeviceToHost, ix->stream));
+  for (int64_t i = 0; i < n; ++i)
+    if (slots[i] < 0 || slots[i] >= ix->n_rows) return fail(RBK_EINVAL, "slot out of range");
+  // one H2D of the slots, one of the rows (chunked through the staging buffer), two kernels per chunk that scatter
+  // into the named slots and skip tombstoned ones on the device, ONE host round trip for the whole batch
+  const size_t row_bytes = static_cast<size_t>(ix->dim) * 8;
+  const int64_t chunk_rows = std::max<int64_t>(1, std::min<int64_t>(n, (64ll << 20) / static_cast<int64_t>(row_bytes)));
+  CK(ix->stage.ensure(static_cast<size_t>(chunk_rows) * row_bytes));
+  CK(ix->d_slots.ensure(static_cast<size_t>(n)));
+  CK(cudaMemcpyAsync(ix->d_slots.p, slots, sizeof(int64_t) * n, cudaMemcpyHostToDevice, ix->stream));
+  CK(cudaMemsetAsync(ix->d_counter, 0, sizeof(int), ix->stream));
+  for (int64_t r0 = 0; r0 < n; r0 += chunk_rows) {
+    const int64_t nr = std::min<int64_t>(chunk_rows, n - r0);
+    CK(cudaMemcpyAsync(ix->stage.p, reinterpret_cast<const unsigned char*>(rows) + static_cast<size_t>(r0) * row_bytes,
+                       static_cast<size_t>(nr) * row_bytes, cudaMemcpyHostToDevice, ix->stream));
+    CK(launch_convert_rows(ix->stage.p, 0, nr, ix->dim, ix->dpad, ix->rows, ix->keep_f64 ? ix->rows_f64 : nullptr,
+                           ix->stream, ix->d_slots.p + r0, ix->dead_bits, ix->d_counter));
+    CK(launch_row_norms(ix->rows, ix->keep_f64 ? ix->rows_f64 : nullptr, 0, nr, ix->dim, ix->dpad, ix->inv_norm,
+                        ix->norm2, ix->d_counter + 1, ix->stream, ix->d_slots.p + r0, ix->dead_bits));
+    ix->stats.kernel_launches += ix->keep_f64 ? 3 : 2;
+  }
+  int dead = 0;
+  CK(cudaMemcpyAsync(&dead, ix->d_counter, sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
   CK(cudaStreamSynchronize(ix->stream));
-  if (word & (1u << (slot & 31))) return fail(RBK_EINVAL, "slot is tombstoned");
-  CK(ix->stage.ensure(static_cast<size_t>(ix->dim) * 8));
-  CK(cudaMemcpyAsync(ix->stage.p, row, static_cast<size_t>(ix->dim) * 8, cudaMemcpyHostToDevice, ix->stream));
-  uint16_t* dst = ix->rows + static_cast<size_t>(slot) * ix->dpad;
-  double* dst64 = ix->keep_f64 ? ix->rows_f64 + static_cast<size_t>(slot) * ix->dim : nullptr;
-  CK(launch_convert_rows(ix->stage.p, 0, 1, ix->dim, ix->dpad, dst, dst64, ix->stream));
-  CK(launch_row_norms(dst, dst64, 1, ix->dim, ix->dpad, ix->inv_norm + slot, ix->norm2 + slot, ix->d_counter + 1,
-                      ix->stream));
-  ix->stats.kernel_launches += 2;
-  CK(cudaStreamSynchronize(ix->stream));
+  if (dead > 0) {
+    // a tombstoned slot stays dead: the host never overwrites a deleted id (S9b: a re-added id is appended)
+    char buf[96];
+    snprintf(buf, sizeof buf, "slot is tombstoned (%d of %lld rows skipped)", dead, static_cast<long long>(n));
+    return fail(RBK_EINVAL, buf);
+  }
   return RBK_OK;
+}
+
+rbk_status rbk_index_overwrite_f64(rbk_index* ix, int64_t slot, const double* row) {
+  if (!row) return fail(RBK_EINVAL, "null argument");
+  return rbk_index_overwrite_f64_batch(ix, &slot, 1, row);
 }
 
 rbk_status rbk_index_tombstone(rbk_index* ix, const int64_t* slots, int64_t n) {

@@ -77,12 +77,19 @@ int scan2_resident_k();   // corpus columns per stage of the resident kernel (64
 // ---- ingest (rbk_ingest.cu) ----
 // src element type: 0 = f64, 1 = f32, 2 = bf16 bits.  src is device memory, row pitch = d.
 // dst_f64 (nullable): exact-source sidecar rows, pitch d.
+// slot_map (nullable, bulk overwrite): dst_rows / dst_f64 are the index's row 0 and source row r lands in row
+// slot_map[r]; rows whose slot is tombstoned (dead_bits) are skipped and counted in *n_dead.
 cudaError_t launch_convert_rows(const void* src, int src_type, int64_t n_rows, int d, int dpad,
-                                uint16_t* dst_rows, double* dst_f64, cudaStream_t stream);
-// rows_f64 (nullable): when given, norm2 comes from it and the bf16-vs-f64 angle bound is max-ed into *eps_c_max
-// (float bits in an int).
-cudaError_t launch_row_norms(const uint16_t* rows, const double* rows_f64, int64_t n_rows, int d, int dpad,
-                             float* inv_norm, double* norm2, int* eps_c_max, cudaStream_t stream);
+                                uint16_t* dst_rows, double* dst_f64, cudaStream_t stream,
+                                const int64_t* slot_map = nullptr, const unsigned int* dead_bits = nullptr,
+                                int* n_dead = nullptr);
+// Norms of rows [first_row, first_row + n_items) of the index (or, with slot_map, of rows slot_map[i]; tombstoned
+// ones skipped).  All array arguments are the index's BASE pointers.  rows_f64_base (nullable): when given,
+// norm2 comes from it and the bf16-vs-f64 angle bound is max-ed into *eps_c_max (float bits in an int).
+cudaError_t launch_row_norms(const uint16_t* rows_base, const double* rows_f64_base, int64_t first_row,
+                             int64_t n_items, int d, int dpad, float* inv_norm_base, double* norm2_base,
+                             int* eps_c_max, cudaStream_t stream, const int64_t* slot_map = nullptr,
+                             const unsigned int* dead_bits = nullptr);
 cudaError_t launch_tombstone(const int64_t* dev_slots, int64_t n, int64_t n_rows, float* inv_norm,
                              unsigned int* dead_bits, int* n_killed, cudaStream_t stream);
 

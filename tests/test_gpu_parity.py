@@ -234,6 +234,49 @@ def test_mutation_sequence_matches_oracle(rb, oracle_mod):
         check_against_oracle(oracle_mod, ix, corpus[:300], q, 5, None)
 
 
+def test_bulk_overwrite_and_device_f64_append_match_oracle(rb, oracle_mod):
+    """addChunks over existing ids (vector-store.ts:135-183) = ONE rbk_index_overwrite_f64_batch call: rows land in
+    their slots, norms are recomputed, tombstoned slots stay dead (and are reported).  Also the device-resident f64
+    append and the ingest kernels on awkward widths (d % 8 != 0, d > one staging chunk, exact-source sidecar)."""
+    import torch
+    from runbookai_b200 import synth
+    rng = np.random.default_rng(301)
+    for d, keep in ((100, False), (776, False), (1536, False), (200, True)):
+        n = 3000
+        corpus_f = synth.bf16_bits_to_f32(synth.random_corpus(n, d, 300 + d)).astype(np.float64)
+        if keep:
+            corpus_f = rng.standard_normal((n, d))          # arbitrary doubles: the sidecar is the exact source
+        q = synth.random_queries(5, d, 302).astype(np.float64)
+        with rb.Index(d, keep_f64=keep, capacity_hint=16) as ix:
+            t = torch.from_numpy(corpus_f[:2000]).cuda()
+            assert ix.append_f64_device(t.data_ptr(), 2000) == 0
+            assert ix.append_f64(corpus_f[2000:]) == 2000
+            dead = rng.choice(n, 200, replace=False)
+            ix.tombstone(dead)
+            live = np.ones(n, dtype=np.uint8)
+            live[dead] = 0
+            slots = np.flatnonzero(live)[rng.choice(n - 200, 700, replace=False)]
+            new = synth.bf16_bits_to_f32(synth.random_corpus(700, d, 303)).astype(np.float64)
+            if keep:
+                new = rng.standard_normal((700, d))
+            new[:5] = q * 3.0                                # planted hits: cosine 1 in the overwritten slots
+            ix.overwrite_f64_batch(slots, new)
+            corpus_f[slots] = new
+            for ms in (None, 0.5):
+                s_, v_, c_, _ = ix.search(q, 24, ms)
+                for b in range(5):
+                    es, ev = oracle_mod.search(corpus_f if keep else
+                                               synth.f32_to_bf16_bits(corpus_f.astype(np.float32)), q[b], 24, ms,
+                                               live=live)
+                    assert c_[b] == len(es) and (s_[b, :len(es)] == es).all() and (v_[b, :len(es)] == ev).all()
+                assert (s_[:, 0] == slots[:5]).all()
+            with pytest.raises(rb.RbkError, match="tombstoned"):   # live slots of the batch are written, dead ones skipped
+                ix.overwrite_f64_batch(np.array([slots[9], dead[0]]), np.stack([q[0], q[0]]))
+            assert ix.search(q[:1], 3, None)[0][0, 0] in (slots[0], slots[9])
+            assert ix.count() == n - 200
+            ix.overwrite_f64_batch(np.zeros(0, dtype=np.int64), np.zeros((0, d)))     # empty batch is a no-op
+
+
 def test_degenerate_inputs_and_errors(rb, native):
     from runbookai_b200 import synth
     d = 32
@@ -373,6 +416,28 @@ def test_logical_shards_and_merge_kernel(rb, oracle_mod, native):
                                     os2.data_ptr(), ov2.data_ptr(), oc2.data_ptr())
     torch.cuda.synchronize()
     assert (os2 == os_).all() and (ov2 == ov).all() and (oc2 == oc).all()
+    # exactness flags travel in the block: out_flags[b] = OR over the shards, out_flags[B] counts dirty queries
+    off_f = native.packed_flags_offset(b, k)
+    packed[1 * blk + off_f:1 * blk + off_f + b * 4].view(torch.int32)[[3, 7]] = 1
+    packed[2 * blk + off_f:2 * blk + off_f + b * 4].view(torch.int32)[7] = 1
+    of = torch.zeros((b + 1,), dtype=torch.int32, device=dev)
+    for rep in (1, 2):
+        native.merge_topk_packed_device(0, torch.cuda.current_stream().cuda_stream, G, b, k, packed.data_ptr(),
+                                        os2.data_ptr(), ov2.data_ptr(), oc2.data_ptr(), of.data_ptr())
+        torch.cuda.synchronize()
+        want = np.zeros(b, dtype=np.int32)
+        want[[3, 7]] = 1
+        assert (of[:b].cpu().numpy() == want).all() and int(of[b]) == 2 * rep      # running count
+    assert (os2 == os_).all() and (ov2 == ov).all() and (oc2 == oc).all()
+    # the enqueue-only search writes results + flags straight into a packed block
+    blk1 = torch.zeros((blk,), dtype=torch.uint8, device=dev)
+    shards[0].search_device_async(qd.data_ptr(), b, k, None, blk1.data_ptr(), blk1.data_ptr() + b * k * 8,
+                                  blk1.data_ptr() + b * k * 16, blk1.data_ptr() + off_f)
+    torch.cuda.synchronize()
+    assert (blk1[:b * k * 8].view(torch.int64).view(b, k) == gs[0]).all()
+    assert (blk1[b * k * 8:b * k * 16].view(torch.float64).view(b, k) == gv[0]).all()
+    assert (blk1[off_f:off_f + b * 4].view(torch.int32) == 0).all()
+    assert shards[0].stats()["scans_timed"] >= 2 and shards[0].stats()["scan_ms_total"] > 0
     for ix in shards:
         ix.close()
 
