@@ -131,6 +131,13 @@ rbk_status rbk_index_search_device(rbk_index* idx, const void* dev_queries_f32, 
                                    double min_score, void* dev_out_slots_i64, void* dev_out_scores_f64,
                                    void* dev_out_counts_i32);
 
+/* More hits than RBK_MAX_K_FETCH (callers of the reference pass limit: 1000, knowledge-context.ts:150): the exact
+ * fp64 cosine of EVERY row, out_scores[b * size() + slot], NaN for tombstoned / zero rows (which the reference's
+ * `>= minScore` drops too, S3).  The host applies the threshold, the stable sort and the cut literally
+ * (vector-store.ts:212-221).  One fp64 pass over the corpus per query: the large-k path, not the hot path. */
+rbk_status rbk_index_exact_scores_f64(rbk_index* idx, const double* queries, int32_t B, int32_t query_dim,
+                                      double* out_scores);
+
 /* Enqueue-only variant: nothing is synchronised, the call returns as soon as the kernels are queued on the index
  * stream, so batches pipeline back to back and an exchange step (all-gather + rbk_merge_topk_packed_device) can be
  * queued behind it without a host round trip in between.  dev_out_flags_i32[B]: 0 = the answer of query b is

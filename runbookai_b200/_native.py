@@ -21,7 +21,7 @@ SYMBOLS = [
     "rbk_index_set_slot_base", "rbk_index_append_f64", "rbk_index_append_f32", "rbk_index_append_bf16",
     "rbk_index_append_bf16_device", "rbk_index_append_f64_device", "rbk_index_overwrite_f64", "rbk_index_overwrite_f64_batch", "rbk_index_tombstone", "rbk_index_clear",
     "rbk_index_count", "rbk_index_size", "rbk_index_dim", "rbk_index_read_rows_bf16", "rbk_index_search_f64",
-    "rbk_index_search_f32", "rbk_index_search_device", "rbk_index_search_device_async", "rbk_merge_topk_device",
+    "rbk_index_search_f32", "rbk_index_exact_scores_f64", "rbk_index_search_device", "rbk_index_search_device_async", "rbk_merge_topk_device",
     "rbk_packed_block_bytes", "rbk_packed_flags_offset",
     "rbk_merge_topk_packed_device", "rbk_index_stats",
     "rbk_index_debug_scores_f32",
@@ -79,6 +79,7 @@ def _load() -> C.CDLL:
     for n in ("rbk_index_search_f64", "rbk_index_search_f32"):
         getattr(lib, n).argtypes = [vp, vp, i32, i32, i32, f64, vp, vp, vp, C.POINTER(C.c_float)]
     lib.rbk_index_search_device.argtypes = [vp, vp, i32, i32, f64, vp, vp, vp]
+    lib.rbk_index_exact_scores_f64.argtypes = [vp, vp, i32, i32, vp]
     lib.rbk_index_search_device_async.argtypes = [vp, vp, i32, i32, f64, vp, vp, vp, vp]
     lib.rbk_merge_topk_device.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.rbk_packed_block_bytes.argtypes = [i32, i32]
@@ -218,6 +219,32 @@ class Index:
         ms_arg = -np.inf if min_score is None else float(min_score)
         check(fn(self._h, ptr(q), B, q.shape[1], k_fetch, ms_arg, ptr(slots), ptr(scores), ptr(counts), C.byref(ms)))
         return slots, scores, counts, ms.value
+
+    def exact_scores(self, queries) -> np.ndarray:
+        """float64 [B, size()]: the reference's cosine of every row, NaN for tombstoned / zero rows (large-k path)."""
+        q = np.ascontiguousarray(np.atleast_2d(np.asarray(queries, dtype=np.float64)))
+        out = np.empty((q.shape[0], self.size()), dtype=np.float64)
+        check(lib.rbk_index_exact_scores_f64(self._h, ptr(q), q.shape[0], q.shape[1], ptr(out)))
+        return out
+
+    def search_any_k(self, queries, k_fetch: int, min_score: float | None = 0.5):
+        """search() for any k_fetch: above RBK_MAX_K_FETCH the answer is cut on the host from exact_scores() with the
+        reference's own steps - `>= minScore`, stable descending sort over slot order, slice (vector-store.ts:212-221)."""
+        if k_fetch <= RBK_MAX_K_FETCH:
+            return self.search(queries, k_fetch, min_score)
+        sc = self.exact_scores(queries)
+        B = sc.shape[0]
+        slots = np.full((B, k_fetch), -1, dtype=np.int64)
+        scores = np.full((B, k_fetch), np.nan, dtype=np.float64)
+        counts = np.zeros(B, dtype=np.int32)
+        for b in range(B):
+            with np.errstate(invalid="ignore"):
+                keep = np.flatnonzero(sc[b] >= min_score) if min_score is not None else np.flatnonzero(~np.isnan(sc[b]))
+            order = keep[np.argsort(-sc[b, keep], kind="stable")][:k_fetch]
+            counts[b] = len(order)
+            slots[b, :len(order)] = order
+            scores[b, :len(order)] = sc[b, order]
+        return slots, scores, counts, 0.0
 
     def search_device(self, q_ptr: int, B: int, k_fetch: int, min_score: float | None, slots_ptr: int,
                       scores_ptr: int, counts_ptr: int) -> None:

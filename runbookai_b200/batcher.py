@@ -34,6 +34,7 @@ class MicroBatcher:
         self.max_batch = max_batch
         self._q: queue.Queue = queue.Queue()
         self._stop = threading.Event()
+        self._close_lock = threading.Lock()
         self.batches = 0          # device passes issued
         self.served = 0           # queries answered
         self._thread = threading.Thread(target=self._run, name="rbk-microbatcher", daemon=True)
@@ -42,16 +43,29 @@ class MicroBatcher:
     # ------------------------------------------------------------------ public
     def submit(self, query: str, options: dict | None = None) -> Future:
         fut: Future = Future()
-        self._q.put((query, dict(options or {}), fut))
+        with self._close_lock:
+            if self._stop.is_set():
+                raise RuntimeError("batcher closed")
+            self._q.put((query, dict(options or {}), fut))
         return fut
 
     def search(self, query: str, options: dict | None = None):
         return self.submit(query, options).result()
 
     def close(self) -> None:
-        self._stop.set()
-        self._q.put(None)
+        """Stop the worker.  Requests still queued are failed with `batcher closed` (nobody is left waiting for a
+        result that will never come); submit() after close raises."""
+        with self._close_lock:
+            self._stop.set()
+            self._q.put(None)
         self._thread.join(timeout=5)
+        while True:
+            try:
+                item = self._q.get_nowait()
+            except queue.Empty:
+                break
+            if item is not None and not item[2].done():
+                item[2].set_exception(RuntimeError("batcher closed"))
 
     # ------------------------------------------------------------------ worker
     def _run(self) -> None:
@@ -79,21 +93,31 @@ class MicroBatcher:
             if not _emb.is_embedder_configured():
                 raise RuntimeError(NOT_CONFIGURED)
             st = self.store
-            qvec = np.asarray(_emb.embed_texts([b[0] for b in batch]), dtype=np.float64)
-            if st._index is None or not st._ids:
-                for _, _, f in batch:
-                    f.set_result([])
+            # callers that want more than the scan's candidate lists hold (topK > 56) take the large-k path of
+            # VectorStore.search on their own; everybody else shares one device pass
+            big = [b for b in batch if 2 * (b[1].get("topK") or b[1].get("top_k") or 10) > RBK_MAX_K_FETCH]
+            for q_, o_, f_ in big:
+                try:
+                    f_.set_result(st.search(q_, o_))
+                except Exception as exc:
+                    f_.set_exception(exc)
+                self.served += 1
+            batch = [b for b in batch if b not in big]
+            if not batch:
                 return
-            if st._ragged or qvec.shape[1] != st._index.dim:
-                raise DimensionError(RBK_EDIM, "Vectors must have the same length")
+            qvec = np.asarray(_emb.embed_texts([b[0] for b in batch]), dtype=np.float64)
             # one device pass: fetch enough for the most demanding caller, strictest-common threshold = the
             # LOWEST minScore; each caller's own cut and threshold are re-applied below (S4, S5, S7)
             top_ks = [o.get("topK") or o.get("top_k") or 10 for _, o, _ in batch]
             mins = [o.get("minScore") or o.get("min_score") or 0.5 for _, o, _ in batch]
             k_fetch = 2 * max(top_ks)
-            if k_fetch > RBK_MAX_K_FETCH:
-                raise ValueError(f"topK {max(top_ks)}: the engine returns at most {RBK_MAX_K_FETCH} (= 2*topK) per query")
-            with st._st.lock:   # scan and slot -> id lookup against the same table (the index may be shared)
+            with st._st.lock:   # state checks, scan and slot -> id lookup against the same table (the index may be shared)
+                if st._index is None or not st._ids:
+                    for _, _, f in batch:
+                        f.set_result([])
+                    return
+                if st._ragged or qvec.shape[1] != st._index.dim:
+                    raise DimensionError(RBK_EDIM, "Vectors must have the same length")
                 slots, scores, counts, _ = st._index.search(qvec, k_fetch, min(mins))
                 picked = []
                 for i in range(len(batch)):

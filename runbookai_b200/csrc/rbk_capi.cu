@@ -153,7 +153,8 @@ struct rbk_index {
   PinBuf<long long> h_slots;
   PinBuf<double> h_scores;
   PinBuf<float> h_f32;
-  CUtensorMap tmap_c, tmap_c_half, tmap_c_half32, tmap_c_pf, tmap_c_r32;
+  CUtensorMap tmap_c, tmap_c_half, tmap_c_quarter, tmap_c_half32, tmap_c_pf, tmap_c_r32;
+  int cluster4 = 1;          // B > 128: clusters of two CTA pairs with one operand multicast (rbk_scan4.cu)
   int perf_probe = 0;
   int max_lead_tiles = kMaxLeadTiles;
   int seed_tile = -1;        // -1 = by unit count; RBK_KNN_SEED_TILE=0|1 forces
@@ -343,6 +344,8 @@ rbk_status refresh_corpus_tmap(rbk_index* ix) {
   if (st != RBK_OK) return st;
   st = encode_rows_tmap(&ix->tmap_c_half, ix->rows, ix->n_rows, ix->dpad, kBlockN / 2);
   if (st != RBK_OK) return st;
+  st = encode_rows_tmap(&ix->tmap_c_quarter, ix->rows, ix->n_rows, ix->dpad, kBlockN / 4);
+  if (st != RBK_OK) return st;
 #ifdef RBK_EXPERIMENTAL
   st = encode_rows_tmap(&ix->tmap_c_half32, ix->rows, ix->n_rows, ix->dpad, kBlockN / 2, 32);
   if (st != RBK_OK) return st;
@@ -414,9 +417,26 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
     const int QB = (Bs + block_m - 1) / block_m;
     const int units = pairs ? ix->sm_count / 2 : ix->sm_count;
     int R = std::max(1, std::min(units / QB, n_tiles));
-    CUtensorMap tmap_q;
+    // B > 128: clusters of two pairs, one operand of every k-block multicast (rbk_scan4.cu).  An even number of
+    // query blocks: the pairs of a cluster take different blocks and share the corpus tile; odd: same block,
+    // alternate tiles, shared query slab.
+    const bool aligned = pairs ? scan_smem_base_is_aligned() : false;
+    const int max_cl = (pairs && ix->cluster4) ? scan4_max_clusters(aligned) : 0;
+    const bool use4 = max_cl > 0;
+    const bool share_c = use4 && (QB % 2) == 0;
+    int RC = 0;
+    if (use4) {
+      const int n_cols = share_c ? QB / 2 : QB;
+      RC = std::max(1, std::min(max_cl / n_cols, share_c ? n_tiles : (n_tiles + 1) / 2));
+      R = share_c ? RC : 2 * RC;
+    }
+    CUtensorMap tmap_q, tmap_q64;
     st = encode_rows_tmap(&tmap_q, ix->q_bf16.p + static_cast<size_t>(q0) * ix->dpad, Bs, ix->dpad, kBlockM);
     if (st != RBK_OK) return st;
+    if (use4) {
+      st = encode_rows_tmap(&tmap_q64, ix->q_bf16.p + static_cast<size_t>(q0) * ix->dpad, Bs, ix->dpad, kBlockM / 2);
+      if (st != RBK_OK) return st;
+    }
     ScanParams sp;
     sp.inv_norm_c = ix->inv_norm;
     sp.thr_init = ix->thr_init.p + q0;
@@ -442,6 +462,7 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
     sp.dpad = ix->dpad;
     sp.QB = QB;
     sp.R = R;
+    sp.RC = RC;
     sp.n_tiles = n_tiles;
     cudaEvent_t* tev = next_scan_events(ix);
     CK(cudaEventRecord(tev[0], ix->stream));
@@ -468,6 +489,10 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
     // 0.07 ms at 65k rows): with one or two tiles per unit and only two seeds from each, a unit that reads the
     // histogram before ~k'/2 peers have seeded finds no threshold and floods its lists.
     sp.seed_tile = ix->seed_tile >= 0 ? ix->seed_tile : ((pairs && R * 2 * halves >= 4 * kprime) ? 1 : 0);
+    if (use4) {
+      CK(launch_scan4(tmap_q, tmap_q64, ix->tmap_c_half, ix->tmap_c_quarter, sp, share_c, aligned, ix->stream,
+                      &ix->stats.last_ring_stages));
+    } else
 #ifdef RBK_EXPERIMENTAL
     if (pairs && !ts && ix->hybrid_res_kb >= 0)
       CK(launch_scan2h(tmap_q, ix->tmap_c_half, sp, ix->hybrid_res_kb, ix->hybrid_slots, ix->stream));
@@ -711,6 +736,7 @@ rbk_status rbk_index_create_ex(int32_t dim, int32_t device, int64_t capacity_hin
   memset(&ix->stats, 0, sizeof ix->stats);
   ix->stats.sm_count = ix->sm_count;
 #ifdef RBK_EXPERIMENTAL   // A/B switches of development builds; the shipped library reads no environment
+  if (const char* m = getenv("RBK_KNN_CLUSTER4")) ix->cluster4 = atoi(m);
   if (const char* m = getenv("RBK_KNN_MARGIN")) ix->margin = std::max(0, std::min(96, atoi(m)));
   if (const char* m = getenv("RBK_KNN_FORCE_1CTA")) ix->force_1cta = atoi(m) != 0;
   if (const char* m = getenv("RBK_KNN_RESIDENT")) ix->force_streamed = atoi(m) == 0;
@@ -943,6 +969,29 @@ rbk_status rbk_index_search_device(rbk_index* ix, const void* dev_queries_f32, i
   return search_core(ix, nullptr, dev_queries_f32, 4, B, ix ? ix->dim : 0, k_fetch, min_score,
                      static_cast<long long*>(dev_out_slots), static_cast<double*>(dev_out_scores),
                      static_cast<int*>(dev_out_counts), nullptr, nullptr, nullptr, nullptr);
+}
+
+rbk_status rbk_index_exact_scores_f64(rbk_index* ix, const double* queries, int32_t B, int32_t query_dim,
+                                      double* out_scores) {
+  if (!ix) return fail(RBK_EINVAL, "null index");
+  if (B < 0 || (B > 0 && (!queries || !out_scores))) return fail(RBK_EINVAL, "bad argument");
+  if (query_dim != ix->dim) return fail(RBK_EDIM, "Vectors must have the same length");  // embedder.ts:170
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard dg(ix->device);
+  if (B == 0 || ix->n_rows == 0) return RBK_OK;
+  rbk_status st = ensure_query_scratch(ix, B, 8);
+  if (st != RBK_OK) return st;
+  const size_t n = static_cast<size_t>(B) * ix->n_rows;
+  CK(ix->o_scores.ensure(n));
+  CK(cudaMemcpyAsync(ix->q_raw.p, queries, static_cast<size_t>(B) * ix->dim * 8, cudaMemcpyHostToDevice, ix->stream));
+  // the prep kernel gives the f64 copy and the reference's normA; its scan-side outputs are unused here
+  CK(launch_prep_queries(ix->q_raw.p, 0, B, ix->dim, ix->dpad, -INFINITY, nullptr, query_buffers(ix, 0), ix->stream));
+  CK(launch_exact_scores(ix->rows, ix->rows_f64, ix->norm2, ix->dead_bits, ix->n_rows, ix->dim, ix->dpad, ix->q_f64.p,
+                         ix->q_norm2.p, B, ix->o_scores.p, ix->stream));
+  ix->stats.kernel_launches += 2;
+  CK(cudaMemcpyAsync(out_scores, ix->o_scores.p, n * 8, cudaMemcpyDeviceToHost, ix->stream));
+  CK(cudaStreamSynchronize(ix->stream));
+  return RBK_OK;
 }
 
 rbk_status rbk_index_search_device_async(rbk_index* ix, const void* dev_queries_f32, int32_t B, int32_t k_fetch,

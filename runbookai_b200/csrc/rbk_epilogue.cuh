@@ -323,11 +323,20 @@ __device__ __forceinline__ void filter_compact_if_needed(FilterState& s, int kpr
 // finalize kernel a unit simply looks like two.  One epilogue warp per SM sub-partition is latency-bound
 // (~0.15 IPC: dependent TMEM-load / multiply / max chains and divergent append blocks with nothing to
 // overlap them); two per sub-partition hide each other's latencies and halve the per-tile work of each.
+// Tile sequence of a unit: tile(it) = t0 + it * t_step for it in [0, n_iter); a tile index >= t1 is a PHANTOM
+// (the cluster kernel keeps its two pairs in step when a range has an odd number of tiles): it is redirected to
+// tile p.n_tiles, whose rows lie beyond n_rows - TMA zero-fills them, their 1/||c|| is the NaN padding of the norm
+// array, so nothing is ever appended from it.
 template <bool kPair, int kHalves = 1>
 __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_stage)[kBlockN],
                                              unsigned long long* tmem_full, unsigned long long* tmem_empty,
                                              uint32_t tmem_base, int qb, int r, uint32_t rank, int t0, int t1,
-                                             int warp, int lane) {
+                                             int warp, int lane, int t_step = 1, int n_iter = -1) {
+  if (n_iter < 0) n_iter = t1 - t0;
+  auto tile_of = [&](int it) {
+    const int t = t0 + it * t_step;
+    return t < t1 ? t : p.n_tiles;
+  };
   constexpr int kEpi = 128 * kHalves;
   constexpr int kBlockQ = kPair ? 2 * kBlockM : kBlockM;
   constexpr int kCols = kBlockN / kHalves;          // columns of a tile this thread filters
@@ -371,29 +380,29 @@ __device__ __forceinline__ void run_epilogue(const ScanParams& p, float (*invc_s
 #endif
   unsigned int* gthr_q = p.gthr + (q_valid ? q : 0);
   unsigned int ngt = 0u;   // published threshold, fetched one tile ahead
-  if (t0 < t1) {
+  if (n_iter > 0) {
 #ifndef RBK_NORMS_L1
-    nx0 = __ldg(p.inv_norm_c + t0 * kBlockN + et);
-    if (kHalves == 1) nx1 = __ldg(p.inv_norm_c + t0 * kBlockN + kEpi + et);
+    nx0 = __ldg(p.inv_norm_c + tile_of(0) * kBlockN + et);
+    if (kHalves == 1) nx1 = __ldg(p.inv_norm_c + tile_of(0) * kBlockN + kEpi + et);
 #else
-    if (lane < kBlockN / 32) prefetch_l1(p.inv_norm_c + static_cast<size_t>(t0) * kBlockN + lane * 32);
+    if (lane < kBlockN / 32) prefetch_l1(p.inv_norm_c + static_cast<size_t>(tile_of(0)) * kBlockN + lane * 32);
 #endif
   }
-  for (int tile = t0; tile < t1; ++tile) {
+  for (int it = 0; it < n_iter; ++it) {
+    const int tile = tile_of(it);
     const int row0 = tile * kBlockN;
-    const int it = tile - t0;
 #ifndef RBK_NORMS_L1
     float* invc = invc_stage[as];
     invc[et] = nx0;
     if (kHalves == 1) invc[kEpi + et] = nx1;
-    if (tile + 1 < t1) {
-      nx0 = __ldg(p.inv_norm_c + (tile + 1) * kBlockN + et);
-      if (kHalves == 1) nx1 = __ldg(p.inv_norm_c + (tile + 1) * kBlockN + kEpi + et);
+    if (it + 1 < n_iter) {
+      nx0 = __ldg(p.inv_norm_c + tile_of(it + 1) * kBlockN + et);
+      if (kHalves == 1) nx1 = __ldg(p.inv_norm_c + tile_of(it + 1) * kBlockN + kEpi + et);
     }
 #else
     const float* invc = p.inv_norm_c + static_cast<size_t>(row0);
-    if (tile + 1 < t1 && lane < kBlockN / 32)
-      prefetch_l1(p.inv_norm_c + static_cast<size_t>(tile + 1) * kBlockN + lane * 32);
+    if (it + 1 < n_iter && lane < kBlockN / 32)
+      prefetch_l1(p.inv_norm_c + static_cast<size_t>(tile_of(it + 1)) * kBlockN + lane * 32);
 #endif
     adopt_threshold(fs, ngt);
     ngt = __ldcg(gthr_q);

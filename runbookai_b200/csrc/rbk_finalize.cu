@@ -588,6 +588,31 @@ __global__ void __launch_bounds__(kExThreads) exact_merge_kernel(ExactParams p) 
   if (tid == 0) p.out_counts[q] = n;
 }
 
+// --------------------------------------------------------------------------- all exact scores (large-k path)
+// One thread per (row, query): the reference's fp64 cosine of EVERY row, NaN for tombstoned / zero rows.  Serves
+// requests for more hits than the scan's candidate lists hold (k_fetch > RBK_MAX_K_FETCH): the host then applies
+// `>= minScore`, the stable sort and the cut literally (vector-store.ts:212-221).  Rare and small (RunbookAI's
+// corpora are 10^4-10^5 chunks when somebody asks for 1000 results), so simplicity wins over bandwidth here.
+__global__ void __launch_bounds__(256) exact_scores_kernel(const uint16_t* __restrict__ rows,
+                                                           const double* __restrict__ rows_f64,
+                                                           const double* __restrict__ row_norm2,
+                                                           const unsigned int* __restrict__ dead_bits, int64_t n_rows,
+                                                           int d, int dpad, const double* __restrict__ q_f64,
+                                                           const double* __restrict__ q_norm2,
+                                                           double* __restrict__ out) {
+  const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int q = blockIdx.y;
+  if (row >= n_rows) return;
+  double sc = __longlong_as_double(0x7FF8000000000000ll);
+  if (!((dead_bits[row >> 5] >> (row & 31)) & 1u)) {
+    const double* qv = q_f64 + static_cast<size_t>(q) * d;
+    const double dot = rows_f64 != nullptr ? exact_dot_f64(qv, rows_f64 + static_cast<size_t>(row) * d, d)
+                                           : exact_dot(qv, rows + static_cast<size_t>(row) * dpad, d);
+    sc = exact_cosine(dot, q_norm2[q], row_norm2[row]);
+  }
+  out[static_cast<size_t>(q) * n_rows + row] = sc;
+}
+
 // --------------------------------------------------------------------------- shard merge
 // Lists are sorted by (score desc, slot asc); slots are globally unique, so the rank of an
 // entry in the merged order is its own index plus, for every other list, the number of
@@ -683,6 +708,16 @@ cudaError_t launch_exact_fallback(const ExactParams& p, cudaStream_t stream) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   exact_merge_kernel<<<p.n_fail, kExThreads, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_exact_scores(const uint16_t* rows, const double* rows_f64, const double* row_norm2,
+                                const unsigned int* dead_bits, int64_t n_rows, int d, int dpad, const double* q_f64,
+                                const double* q_norm2, int B, double* out, cudaStream_t stream) {
+  if (B <= 0 || n_rows <= 0) return cudaSuccess;
+  dim3 grid(static_cast<unsigned>((n_rows + 255) / 256), static_cast<unsigned>(B));
+  exact_scores_kernel<<<grid, 256, 0, stream>>>(rows, rows_f64, row_norm2, dead_bits, n_rows, d, dpad, q_f64, q_norm2,
+                                                out);
   return cudaGetLastError();
 }
 

@@ -110,6 +110,24 @@ __device__ __forceinline__ double bf16_bits_to_f64(uint32_t h) {
   return static_cast<double>(__uint_as_float(h << 16));
 }
 
+// x*x of a bf16 value as the binary64 the reference's `b[i] * b[i]` produces (embedder.ts:180) - exactly.  The
+// product of two 8-bit significands has 16 bits, so it is exact in binary32 as well as in binary64: for the values
+// embeddings actually take (2^-60 <= |x| <= 2^60, or 0) it is formed with ONE fp32 multiply and widened with integer
+// shifts, instead of two F2F.F64 conversions and a DMUL per element on the (narrow) fp64 pipe; anything else (tiny,
+// huge, inf, NaN) takes the literal convert-and-multiply path.  Either way the result is the correctly rounded
+// (= exact) product, so norm2 stays bit-identical to the oracle's normB.
+__device__ __forceinline__ double bf16_square_f64(uint32_t h) {
+  const uint32_t e = (h >> 7) & 0xFFu;
+  if (e - 67u <= 120u) {                                   // 2^-60 <= |x| < 2^61: x*x is a normal fp32, no rounding
+    const float x = __uint_as_float(h << 16);
+    const uint32_t b = __float_as_uint(x * x);             // sign 0
+    return __hiloint2double(static_cast<int>((b >> 3) + 0x38000000u), static_cast<int>(b << 29));
+  }
+  if ((h & 0x7FFFu) == 0u) return 0.0;
+  const double x = static_cast<double>(__uint_as_float(h << 16));
+  return __dmul_rn(x, x);
+}
+
 // ---- K3b: per-row norms.  The accumulation ORDER is part of the parity contract (norm2 must be the reference's
 // normB, embedder.ts:180: index order, multiply then add), so each row is one sequential fp64 chain owned by one
 // thread - but the chain must not wait on memory, and the loads must be coalesced.  A block of kNormRows threads
@@ -123,7 +141,7 @@ __device__ __forceinline__ double bf16_bits_to_f64(uint32_t h) {
 // slot_map[i]; items whose slot is tombstoned are skipped.
 constexpr int kNormRows = 128;          // rows (= threads) per block
 constexpr int kNormChunk = 128;         // bf16 elements per staged chunk (256 B per row)
-constexpr int kNormPitch16 = kNormChunk / 8 + 1;   // 17 x 16 B per row in smem
+constexpr int kNormPitch16 = kNormChunk / 8 + 1;   // 17 x 16 B per row in smem: odd -> conflict-free walks
 
 __global__ void __launch_bounds__(kNormRows) row_norms_kernel(const uint16_t* __restrict__ rows_base,
                                                               const double* __restrict__ rows_f64_base,
@@ -150,42 +168,45 @@ __global__ void __launch_bounds__(kNormRows) row_norms_kernel(const uint16_t* __
   const long long my_row = s_row[tid];
   double acc = 0.0;
   const int n16 = dpad >> 3;                         // 16-byte pieces per row
-  for (int c0 = 0; c0 < n16; c0 += kNormChunk / 8) {
-    const int len16 = n16 - c0 < kNormChunk / 8 ? n16 - c0 : kNormChunk / 8;
-    // stage: piece index i -> (row i / len16, unit i % len16); consecutive lanes = consecutive units of a row
-    for (int i0 = tid; i0 < kNormRows * len16; i0 += 8 * kNormRows) {
-      uint4 v[8];
+  constexpr int kPieces = kNormChunk / 8;            // 16-byte pieces per row and chunk; = pieces per thread and chunk
+  // piece index i of a chunk -> (row i / len16, unit i % len16): consecutive lanes = consecutive units of a row.
+  // The NEXT chunk's pieces travel in registers while this chunk is walked, so HBM latency overlaps the chains.
+  uint4 v[kPieces];
+  auto load_chunk = [&](int c0) {
+    const int len16 = n16 - c0 < kPieces ? n16 - c0 : kPieces;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = i0 + u * kNormRows;
-        v[u] = make_uint4(0u, 0u, 0u, 0u);
-        if (i < kNormRows * len16) {
-          const int rr = i / len16, un = i - rr * len16;
-          const long long row = s_row[rr];
-          if (row >= 0) v[u] = __ldg(reinterpret_cast<const uint4*>(rows_base + row * dpad) + c0 + un);
-        }
+    for (int u = 0; u < kPieces; ++u) {
+      const int i = tid + u * kNormRows;
+      v[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (i < kNormRows * len16) {
+        const int rr = i / len16, un = i - rr * len16;
+        const long long row = s_row[rr];
+        if (row >= 0) v[u] = __ldg(reinterpret_cast<const uint4*>(rows_base + row * dpad) + c0 + un);
       }
+    }
+  };
+  load_chunk(0);
+  for (int c0 = 0; c0 < n16; c0 += kPieces) {
+    const int len16 = n16 - c0 < kPieces ? n16 - c0 : kPieces;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = i0 + u * kNormRows;
-        if (i < kNormRows * len16) {
-          const int rr = i / len16, un = i - rr * len16;
-          s_chunk[rr * kNormPitch16 + un] = v[u];
-        }
+    for (int u = 0; u < kPieces; ++u) {
+      const int i = tid + u * kNormRows;
+      if (i < kNormRows * len16) {
+        const int rr = i / len16, un = i - rr * len16;
+        s_chunk[rr * kNormPitch16 + un] = v[u];
       }
     }
     __syncthreads();
+    if (c0 + kPieces < n16) load_chunk(c0 + kPieces);
     if (my_row >= 0) {
       const uint4* mine = s_chunk + tid * kNormPitch16;
       for (int g = 0; g < len16; ++g) {   // pad columns are zero: adding 0*0 is exact
-        const uint4 v = mine[g];
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const uint4 w4 = mine[g];
+        const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const double lo = bf16_bits_to_f64(w[j] & 0xFFFFu);
-          const double hi = bf16_bits_to_f64(w[j] >> 16);
-          acc = __dadd_rn(acc, __dmul_rn(lo, lo));
-          acc = __dadd_rn(acc, __dmul_rn(hi, hi));
+          acc = __dadd_rn(acc, bf16_square_f64(w[j] & 0xFFFFu));
+          acc = __dadd_rn(acc, bf16_square_f64(w[j] >> 16));
         }
       }
     }

@@ -51,7 +51,9 @@ struct ScanParams {
   int seed_tile;       // start-up seeding: 1 = count each thread's two best rows of its first tile, 0 = two per chunk
   int perf_probe;      // 0 = normal.  TIMING EXPERIMENTS ONLY (results are wrong): 1 = epilogue drains TMEM but does not filter
   int QB;       // query blocks
-  int R;        // corpus ranges (CTAs per query block)
+  int R;        // list units per query block (CTAs / CTA pairs that scan different tiles for the same queries)
+  int RC;       // cluster kernel: corpus ranges = clusters per column (R = RC when the pairs of a cluster share the
+                // corpus tile, 2 * RC when they share the query slab and alternate tiles)
   int n_tiles;  // ceil(n_rows / kBlockN)
 };
 
@@ -64,6 +66,13 @@ size_t scan_smem_bytes();
 cudaError_t launch_scan2(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const CUtensorMap& tmap_pf,
                          const ScanParams& p, bool resident, int halves, cudaStream_t stream,
                          int* ring_stages_out = nullptr);
+// Cluster-of-two-pairs kernel with one operand multicast (rbk_scan4.cu).  tmap_q128 / tmap_c128: 128-row boxes,
+// tmap_q64 / tmap_c64: 64-row boxes (the multicast halves), all 64 columns / SWIZZLE_128B.
+cudaError_t launch_scan4(const CUtensorMap& tmap_q128, const CUtensorMap& tmap_q64, const CUtensorMap& tmap_c128,
+                         const CUtensorMap& tmap_c64, const ScanParams& p, bool share_c, bool smem_aligned,
+                         cudaStream_t stream, int* ring_stages_out = nullptr);
+int scan4_max_clusters(bool smem_aligned);   // resident 4-CTA clusters of that kernel on the current device
+bool scan_smem_base_is_aligned();            // is the dynamic smem window 1024-byte aligned (7-stage ring possible)?
 // CTA-pair kernel with the query operand in TMEM (rbk_scan3.cu): dpad <= 768.  tmap_c: 32-row x 64-col boxes.
 cudaError_t launch_scan3(const CUtensorMap& tmap_c, const ScanParams& p, const uint16_t* q_bf16, cudaStream_t stream);
 bool scan3_fits(int dpad);
@@ -150,6 +159,11 @@ struct ExactParams {
   int* out_counts;
 };
 cudaError_t launch_exact_fallback(const ExactParams& p, cudaStream_t stream);
+
+// Exact fp64 cosine of every row for B prepared queries: out [B][n_rows], NaN = tombstoned / zero row.
+cudaError_t launch_exact_scores(const uint16_t* rows, const double* rows_f64, const double* row_norm2,
+                                const unsigned int* dead_bits, int64_t n_rows, int d, int dpad, const double* q_f64,
+                                const double* q_norm2, int B, double* out, cudaStream_t stream);
 
 // slots/scores/counts/flags point at shard 0's arrays; shard g's arrays start g * <stride> bytes later.
 // flags (nullable): per-shard exactness flags i32[B]; out_flags: i32[B+1] ([b] = OR over shards, [B] += dirty queries).

@@ -199,6 +199,19 @@ __device__ __forceinline__ void tma_load_2d_2cta(uint32_t smem_dst, const void* 
       : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(local_bar & kPeerBitMask), "r"(crd0), "r"(crd1)
       : "memory");
 }
+// The same load, MULTICAST: the box is written at the same smem offset of every CTA in cta_mask (bit i = cluster
+// rank i) with ONE read of L2, and each destination's bytes are accounted on the barrier at this offset in the
+// leader (even rank) of THAT destination's pair.
+__device__ __forceinline__ void tma_load_2d_2cta_mc(uint32_t smem_dst, const void* tmap, uint32_t local_bar,
+                                                    int32_t crd0, int32_t crd1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(local_bar & kPeerBitMask), "h"(cta_mask),
+        "r"(crd0), "r"(crd1)
+      : "memory");
+}
 // D[tmem of both CTAs] (+)= A[smem, 128 rows per CTA] * B[smem, N/2 rows per CTA]^T; M = 256.
 __device__ __forceinline__ void umma_bf16_ss_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                                   uint32_t idesc, uint32_t accumulate) {
@@ -216,6 +229,15 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
       :
       : "r"(bar), "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+
+// Same, to the CTAs named by cta_mask (bit i = cluster rank i): clusters of more than one pair.
+__device__ __forceinline__ void umma_commit_2cta_mask(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      :
+      : "r"(bar), "h"(cta_mask)
       : "memory");
 }
 

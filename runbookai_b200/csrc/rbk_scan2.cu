@@ -431,6 +431,9 @@ scan2h_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 
 }  // namespace
 
+// (exported for the cluster kernel's launch, rbk_scan4.cu)
+bool scan_smem_base_is_aligned() { return smem_base_is_aligned(); }
+
 // Can the query block stay resident for this padded dim?
 int scan2_resident_k() { return kKR; }
 

@@ -118,7 +118,8 @@ class MultiDeviceIndex:
             q = q[None, :]
         if q.shape[1] != self.dim:
             raise DimensionError(RBK_EDIM, "Vectors must have the same length")
-        res = list(self._pool.map(lambda p: p.search(q, k_fetch, min_score), self.parts))
+        # any k: beyond the scan's candidate lists every device answers from its exact scores (Index.search_any_k)
+        res = list(self._pool.map(lambda p: getattr(p, "search_any_k", p.search)(q, k_fetch, min_score), self.parts))
         B, G = q.shape[0], len(self.parts)
         slots = np.concatenate([self._global(g, r[0]) for g, r in enumerate(res)], axis=1)      # [B, G*k]
         scores = np.concatenate([r[1] for r in res], axis=1)
@@ -134,6 +135,8 @@ class MultiDeviceIndex:
         out_s[tail] = -1
         out_v[tail] = np.nan
         return out_s, out_v, counts, max(r[3] for r in res)
+
+    search_any_k = search
 
     def stats(self) -> dict:
         per = [p.stats() for p in self.parts]

@@ -94,7 +94,8 @@ class _IndexState:
         self.index: Index | None = None
         self.ids: list[str | None] = []      # slot -> id (None = deleted)
         self.slot_of: dict[str, int] = {}    # live id -> slot  (the reference's Map keys)
-        self.ragged = False                  # stored rows of differing length -> search throws (S2)
+        self.bad_ids: set[str] = set()       # ids whose stored vector has another length: while any is in the
+        #                                      Map the reference's search throws (S2); deleting / re-setting it heals
 
 
 _SHARED: dict[tuple[str, int], _IndexState] = {}
@@ -133,8 +134,29 @@ class VectorStore:
             self._st = _IndexState()
         with self._st.lock:                  # a second opener waits for the first one's load
             if not self._st.loaded:
-                self._load_embeddings()
-                self._st.loaded = True
+                try:
+                    self._load_embeddings()
+                    self._st.loaded = True
+                except BaseException:
+                    # a half-built shared state must not be found by the next opener: drop it, the device index and
+                    # the connection, then let the caller see the error (e.g. cudaMalloc failed mid-append)
+                    st = self._st
+                    if st.key is not None:
+                        with _SHARED_LOCK:
+                            st.refs -= 1
+                            if _SHARED.get(st.key) is st:
+                                _SHARED.pop(st.key, None)
+                    if st.index is not None:
+                        try:
+                            st.index.close()
+                        finally:
+                            st.index = None
+                    st.ids.clear()
+                    st.slot_of.clear()
+                    st.bad_ids.clear()
+                    self._closed = True
+                    self.db.close()
+                    raise
 
     # the state lives in self._st so that instances on the same db can share it
     @property
@@ -154,12 +176,9 @@ class VectorStore:
         return self._st.slot_of
 
     @property
-    def _ragged(self):
-        return self._st.ragged
-
-    @_ragged.setter
-    def _ragged(self, v):
-        self._st.ragged = v
+    def _ragged(self) -> bool:
+        """`Vectors must have the same length` is thrown exactly while a mismatched embedding is in the Map."""
+        return bool(self._st.bad_ids)
 
     # ------------------------------------------------------------------ setup
     def _init_schema(self) -> None:
@@ -177,25 +196,33 @@ class VectorStore:
             return
         dim = len(rows[0]["embedding"]) // 8
         good = [r for r in rows if len(r["embedding"]) == dim * 8]
-        self._ragged = len(good) != len(rows)
+        self._st.bad_ids.update(r["id"] for r in rows if len(r["embedding"]) != dim * 8)
         ix = self._ensure_index(dim)
         step = max(1, (32 << 20) // (dim * 8))
         for r0 in range(0, len(good), step):
             blob = b"".join(r["embedding"] for r in good[r0:r0 + step])
-            ix.append_f64(np.frombuffer(blob, dtype="<f8").reshape(-1, dim))
-        for r in good:
-            self._slot_of[r["id"]] = len(self._ids)
-            self._ids.append(r["id"])
+            first = ix.append_f64(np.frombuffer(blob, dtype="<f8").reshape(-1, dim))
+            for i, r in enumerate(good[r0:r0 + step]):   # the slot the ENGINE assigned, not a private count
+                while len(self._ids) < first + i:
+                    self._ids.append(None)
+                self._slot_of[r["id"]] = first + i
+                self._ids.append(r["id"])
 
     # ------------------------------------------------------------------ mutation
     def _set(self, vid: str, embedding) -> None:
         """`this.embeddings.set(id, embedding)` (vector-store.ts:129,178)."""
         e = np.asarray(embedding, dtype=np.float64)
         ix = self._ensure_index(e.shape[0])
-        if e.shape[0] != ix.dim:
-            self._ragged = True   # the reference would store it and throw on the next search
-            return
         slot = self._slot_of.get(vid)
+        if e.shape[0] != ix.dim:
+            # the reference stores it and throws on every search until the id is deleted or re-set correctly
+            self._st.bad_ids.add(vid)
+            if slot is not None:          # the old, well-formed vector is no longer in the Map either
+                self._slot_of.pop(vid, None)
+                self._ids[slot] = None
+                ix.tombstone([slot])
+            return
+        self._st.bad_ids.discard(vid)
         if slot is not None:
             ix.overwrite_f64(slot, e)     # existing key keeps its Map position (S9b)
         else:
@@ -273,6 +300,7 @@ class VectorStore:
         rows = self.db.execute("SELECT id FROM vector_embeddings WHERE document_id = ?", (document_id,)).fetchall()
         slots = []
         for r in rows:
+            self._st.bad_ids.discard(r["id"])
             s = self._slot_of.pop(r["id"], None)
             if s is not None:
                 self._ids[s] = None
@@ -298,7 +326,7 @@ class VectorStore:
                 self.db.execute("DELETE FROM vector_embeddings")
             self._ids.clear()
             self._slot_of.clear()
-            self._ragged = False
+            self._st.bad_ids.clear()
             if self._index is not None:
                 self._index.clear()
 
@@ -338,8 +366,6 @@ class VectorStore:
         min_score = o.get("minScore") or o.get("min_score") or 0.5   # :202  (0/None -> 0.5)
         type_filter = o.get("typeFilter") or o.get("type_filter")
         service_filter = o.get("serviceFilter") or o.get("service_filter")
-        if 2 * top_k > RBK_MAX_K_FETCH:
-            raise ValueError(f"topK {top_k}: the engine returns at most {RBK_MAX_K_FETCH} (= 2*topK) per query")
         q = np.asarray(_emb.embed_texts(list(queries)) if len(queries) > 1 else [_emb.embed_text(queries[0])],
                        dtype=np.float64)                              # :205
         with self._st.lock:   # the slot table must be the one the scan ran against
@@ -348,7 +374,10 @@ class VectorStore:
             if self._ragged or q.shape[1] != self._index.dim:
                 raise DimensionError(RBK_EDIM, "Vectors must have the same length")   # embedder.ts:170
             # :207-221 — scan, `>= minScore`, stable sort desc, first 2*topK: one device call
-            slots, scores, counts, _ = self._index.search(q, 2 * top_k, min_score)
+            # (2*topK beyond the scan's candidate lists - limit: 50 / 1000 call sites, infra-context.ts:229,
+            # knowledge-context.ts:150 - takes the exact-scores path: same answer, one fp64 pass per query)
+            search = getattr(self._index, "search_any_k", None) if 2 * top_k > RBK_MAX_K_FETCH else None
+            slots, scores, counts, _ = (search or self._index.search)(q, 2 * top_k, min_score)
             ids = [[self._ids[int(s)] for s in slots[b, :counts[b]]] for b in range(len(queries))]
         return [self._hydrate(ids[b], scores[b, :counts[b]], top_k, type_filter, service_filter)
                 for b in range(len(queries))]

@@ -314,3 +314,96 @@ def test_multi_device_index_equals_one_index(oracle_mod):
     multi.clear()
     assert multi.size() == 0 and multi.search(q, 4, None)[2].tolist() == [0, 0, 0, 0]
     multi.close()
+
+
+def test_large_limits_do_not_throw_and_match_the_reference_cut(store, tmp_path):
+    """Reference call sites pass limit: 50 (infra-context.ts:229) and limit: 1000 (knowledge-context.ts:150): topK beyond
+    the scan's candidate lists (2*topK > 112) must return what vector-store.ts:201-279 returns, not raise - through
+    VectorStore.search, the micro-batcher and KnowledgeRetriever (which doubles topK again inside HybridRetriever)."""
+    from oracle import pyref
+    from runbookai_b200 import embedder
+    from runbookai_b200.batcher import MicroBatcher
+    from runbookai_b200.retriever import KnowledgeRetriever
+    for d_i in range(8):
+        store.add_chunks(_chunks(40, f"doc{d_i}", "runbook", ("api",), text=f"redis connection pool exhausted variant {d_i}"))
+    q = "redis connection pool exhausted"
+    rows = store.db.execute("SELECT id, embedding FROM vector_embeddings").fetchall()
+    table = [(r["id"], np.frombuffer(r["embedding"], "<f8").tolist()) for r in rows]
+    for top_k in (57, 100, 1000):
+        res = store.search(q, {"topK": top_k, "minScore": 0.2})
+        ref = pyref.vector_scan(embedder.embed_text(q), table, top_k=top_k, min_score=0.2)[:top_k]
+        assert [f"vec_{r.id}" for r in res] == [i for i, _ in ref] and [r.score for r in res] == [s for _, s in ref]
+    mb = MicroBatcher(store, window_ms=20.0)
+    f_small, f_big = mb.submit(q, {"topK": 5, "minScore": 0.2}), mb.submit(q, {"topK": 300, "minScore": 0.2})
+    assert f_big.result(timeout=30) == store.search(q, {"topK": 300, "minScore": 0.2})
+    assert f_small.result(timeout=30) == store.search(q, {"topK": 5, "minScore": 0.2})
+    mb.close()
+    r = KnowledgeRetriever({"storePath": str(tmp_path / "kr" / "knowledge.db"), "sources": []}, vector_store=store)
+    for limit in (50, 1000):
+        k = r.search(q, {"limit": limit})
+        assert set(k) == {"runbooks", "postmortems", "architecture", "knownIssues"} and len(k["runbooks"]) > 28
+    r.store.close()
+
+
+def test_mismatched_length_embedding_throws_only_while_it_is_in_the_map(store):
+    """embedder.ts:169-171 throws while a wrong-length vector is stored; deleteDocument of that doc, or re-setting the
+    id with a correct vector, makes search work again (the flag used to stick until clear())."""
+    from runbookai_b200 import embedder
+    from runbookai_b200._native import DimensionError
+    store.add_chunks(_chunks(3, "docA"))
+    q = "redis connection pool exhausted"
+    assert len(store.search(q, {"minScore": 0.2})) == 3
+    embedder.configure(HashEmbedder(48))                       # the embedder now returns another dimension
+    store.add_chunk({"id": "docB_0", "documentId": "docB", "content": "redis pool", "sectionTitle": "S"}, "B", "runbook", [])
+    store.add_chunk(_chunks(1, "docA")[0]["chunk"], "Title docA", "runbook", ["api"])   # re-set docA_0 with a bad length
+    embedder.configure(HashEmbedder(64))
+    with pytest.raises(DimensionError, match="Vectors must have the same length"):
+        store.search(q, {"minScore": 0.2})
+    store.delete_document("docB")                              # one offender gone, the re-set docA_0 still offends
+    with pytest.raises(DimensionError):
+        store.search(q, {"minScore": 0.2})
+    store.add_chunk(_chunks(1, "docA")[0]["chunk"], "Title docA", "runbook", ["api"])   # re-set correctly: healed
+    res = store.search(q, {"minScore": 0.2})
+    assert sorted(r.id for r in res) == ["docA_0", "docA_1", "docA_2"]
+    assert store._index.count() == 3                           # the stale vector of docA_0 was tombstoned, not kept
+
+
+def test_failed_load_does_not_leave_a_half_built_shared_index(tmp_path):
+    """If the bulk load of a shared store fails (e.g. cudaMalloc mid-append), the registry entry, the device index and
+    the connection are dropped; the next opener loads from scratch instead of attaching to a half-filled index."""
+    from runbookai_b200 import embedder
+    from runbookai_b200.vector_store import create_vector_store, shared_index_count
+    embedder.configure(HashEmbedder(64))
+    base = str(tmp_path)
+    s = create_vector_store(base, index_factory=lambda d, dev: OracleIndex(d))
+    s.add_chunks(_chunks(5, "docA"))
+    s.close()
+    assert shared_index_count() == 0
+
+    class Exploding(OracleIndex):
+        def append_f64(self, rows):
+            raise MemoryError("cudaMalloc failed")
+    with pytest.raises(MemoryError):
+        create_vector_store(base, index_factory=lambda d, dev: Exploding(d))
+    assert shared_index_count() == 0
+    s2 = create_vector_store(base, index_factory=lambda d, dev: OracleIndex(d))
+    assert len(s2.search("redis connection pool exhausted", {"minScore": 0.2})) == 5
+    s2.close()
+    embedder.reset()
+
+
+def test_micro_batcher_close_fails_queued_requests_and_rejects_new_ones(store):
+    from runbookai_b200.batcher import MicroBatcher
+    store.add_chunks(_chunks(3, "docA"))
+    mb = MicroBatcher(store, window_ms=1.0)
+    assert len(mb.search("redis connection pool exhausted", {"minScore": 0.2})) == 3
+    mb.close()
+    with pytest.raises(RuntimeError, match="batcher closed"):
+        mb.submit("anything")
+    # a request that slipped in behind the stop sentinel is failed, not left pending
+    from concurrent.futures import Future
+    fut = Future()
+    mb._q.put(("late", {}, fut))
+    mb.close()
+    with pytest.raises(RuntimeError, match="batcher closed"):
+        fut.result(timeout=1)
