@@ -19,9 +19,10 @@
  *   - Every function returns rbk_status; on failure rbk_last_error() holds the message
  *     the binding turns into `new Error(msg)`.  Nothing throws or aborts.
  *   - Inputs are borrowed for the duration of the call; outputs are caller-allocated.
- *   - An index is bound to ONE GPU.  A corpus sharded over several GPUs is one index
- *     per GPU (one process per GPU, or several indexes in one process) plus
- *     rbk_merge_topk_device() after the exchange of the per-shard lists.
+ *   - An index is bound to ONE GPU.  A corpus sharded over several GPUs is either a
+ *     group - rbk_group_*: one process, one handle, NCCL all-gather inside the search call - or one
+ *     index per GPU in one process per GPU plus rbk_merge_topk_packed_device() after the
+ *     caller's own exchange of the per-shard blocks.
  *   - Thread safety: calls on the same index are serialised by an internal mutex;
  *     different indexes are independent.
  *   - There is NO CPU fallback: without a CUDA device rbk_index_create fails with
@@ -48,7 +49,7 @@ typedef enum {
   RBK_EINVAL = 1, /* bad argument */
   RBK_ENOMEM = 2, /* host or device allocation failed */
   RBK_ECUDA = 3,  /* CUDA runtime/driver error, or no device */
-  RBK_ENCCL = 4,  /* reserved for the in-library collective path */
+  RBK_ENCCL = 4,  /* NCCL missing or failing (rbk_group_* with more than one GPU) */
   RBK_EDIM = 5    /* "Vectors must have the same length" (embedder.ts:169-171) */
 } rbk_status;
 
@@ -169,6 +170,38 @@ int64_t rbk_packed_flags_offset(int32_t B, int32_t k_fetch);
 rbk_status rbk_merge_topk_packed_device(int32_t device, void* cuda_stream, int32_t G, int32_t B, int32_t k_fetch,
                                         const void* dev_blocks, void* dev_out_slots_i64, void* dev_out_scores_f64,
                                         void* dev_out_counts_i32, void* dev_out_flags_i32);
+
+/* ---- one corpus over several GPUs behind ONE handle (rbk_group.cu) ----
+ * What a single host process (RunbookAI is one Node process) uses to shard `this.embeddings` over the GPUs of a
+ * box: one index per device, rows dealt out block-cyclically (4096-row blocks, so the corpus may grow at sync
+ * time), every search = H2D of the queries to every GPU, the fused scan on every GPU, ONE ncclAllGather of the packed
+ * per-GPU blocks over NVLink, a merge kernel on device_ids[0], one D2H and ONE host synchronisation - all inside
+ * rbk_group_search_*.  Slots are GLOBAL insertion indices, exactly as for a single index; results are identical
+ * to a single index holding the same rows (ids and fp64 scores bit for bit, ties by ascending slot).
+ * NCCL is looked up at run time (dlopen "libnccl.so.2"); a group of more than one GPU fails with RBK_ENCCL if it
+ * is missing, a one-GPU group never touches it.  Mutation and search semantics, limits (k_fetch <= RBK_MAX_K_FETCH)
+ * and error conventions are those of the rbk_index_* call of the same name. */
+typedef struct rbk_group rbk_group;
+rbk_status rbk_group_create(int32_t dim, const int32_t* device_ids, int32_t n_devices, int64_t capacity_hint,
+                            uint32_t flags /* RBK_INDEX_KEEP_F64 */, rbk_group** out);
+void rbk_group_destroy(rbk_group* grp); /* NULL is a no-op */
+rbk_status rbk_group_append_f64(rbk_group* grp, const double* rows, int64_t n_rows, int64_t* first_slot_out);
+rbk_status rbk_group_append_f32(rbk_group* grp, const float* rows, int64_t n_rows, int64_t* first_slot_out);
+rbk_status rbk_group_append_bf16(rbk_group* grp, const uint16_t* rows, int64_t n_rows, int64_t* first_slot_out);
+rbk_status rbk_group_overwrite_f64_batch(rbk_group* grp, const int64_t* slots, int64_t n, const double* rows);
+rbk_status rbk_group_tombstone(rbk_group* grp, const int64_t* slots, int64_t n);
+rbk_status rbk_group_clear(rbk_group* grp);
+int64_t rbk_group_count(const rbk_group* grp); /* live rows */
+int64_t rbk_group_size(const rbk_group* grp);  /* slots used, tombstones included */
+int32_t rbk_group_devices(const rbk_group* grp);
+rbk_index* rbk_group_member(rbk_group* grp, int32_t i); /* the i-th device's index (stats, tests); owned by the group */
+int64_t rbk_group_redone_batches(const rbk_group* grp); /* batches re-answered because a shard's proof failed */
+rbk_status rbk_group_search_f32(rbk_group* grp, const float* queries, int32_t B, int32_t query_dim, int32_t k_fetch,
+                                double min_score, int64_t* out_slots, double* out_scores, int32_t* out_counts,
+                                float* device_ms_out);
+rbk_status rbk_group_search_f64(rbk_group* grp, const double* queries, int32_t B, int32_t query_dim, int32_t k_fetch,
+                                double min_score, int64_t* out_slots, double* out_scores, int32_t* out_counts,
+                                float* device_ms_out);
 
 /* ---- introspection ---- */
 typedef struct {

@@ -13,7 +13,7 @@ runbookai_b200/lib/librbk_knn.so on first use and fails loudly if it has not bee
 (there is no CPU or library fallback).  The numpy-only helpers (`synth`, `build`) import
 without the library.
 """
-__all__ = ["Index", "RbkError", "DimensionError"]
+__all__ = ["Index", "Group", "RbkError", "DimensionError"]
 
 
 def __getattr__(name):   # PEP 562: `from runbookai_b200 import Index` loads the .so, `import runbookai_b200.synth` does not

@@ -25,6 +25,9 @@ SYMBOLS = [
     "rbk_packed_block_bytes", "rbk_packed_flags_offset",
     "rbk_merge_topk_packed_device", "rbk_index_stats",
     "rbk_index_debug_scores_f32",
+    "rbk_group_create", "rbk_group_destroy", "rbk_group_append_f64", "rbk_group_append_f32", "rbk_group_append_bf16",
+    "rbk_group_overwrite_f64_batch", "rbk_group_tombstone", "rbk_group_clear", "rbk_group_count", "rbk_group_size",
+    "rbk_group_devices", "rbk_group_member", "rbk_group_redone_batches", "rbk_group_search_f32", "rbk_group_search_f64",
 ]
 
 
@@ -88,6 +91,23 @@ def _load() -> C.CDLL:
     lib.rbk_packed_flags_offset.restype = i64
     lib.rbk_merge_topk_packed_device.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.rbk_index_stats.argtypes = [vp, C.POINTER(RbkStats)]
+    lib.rbk_group_create.argtypes = [i32, vp, i32, i64, C.c_uint32, C.POINTER(vp)]
+    lib.rbk_group_destroy.argtypes = [vp]
+    lib.rbk_group_destroy.restype = None
+    for n in ("rbk_group_append_f64", "rbk_group_append_f32", "rbk_group_append_bf16"):
+        getattr(lib, n).argtypes = [vp, vp, i64, C.POINTER(i64)]
+    lib.rbk_group_overwrite_f64_batch.argtypes = [vp, vp, i64, vp]
+    lib.rbk_group_tombstone.argtypes = [vp, vp, i64]
+    lib.rbk_group_clear.argtypes = [vp]
+    for n in ("rbk_group_count", "rbk_group_size", "rbk_group_redone_batches"):
+        getattr(lib, n).argtypes = [vp]
+        getattr(lib, n).restype = i64
+    lib.rbk_group_devices.argtypes = [vp]
+    lib.rbk_group_devices.restype = i32
+    lib.rbk_group_member.argtypes = [vp, i32]
+    lib.rbk_group_member.restype = vp
+    for n in ("rbk_group_search_f32", "rbk_group_search_f64"):
+        getattr(lib, n).argtypes = [vp, vp, i32, i32, i32, f64, vp, vp, vp, C.POINTER(C.c_float)]
     lib.rbk_index_debug_scores_f32.argtypes = [vp, vp, i32, vp]
     return lib
 
@@ -270,6 +290,104 @@ class Index:
         st = RbkStats()
         check(lib.rbk_index_stats(self._h, C.byref(st)))
         return {f: getattr(st, f) for f, _ in RbkStats._fields_}
+
+
+class Group:
+    """rbk_group*: one corpus sharded over several GPUs behind one handle; the Index surface with GLOBAL slots.
+    Every search is one C call: per-GPU scans, one NCCL all-gather, merge on devices[0], one synchronisation."""
+
+    def __init__(self, dim: int, devices, capacity_hint: int = 0, keep_f64: bool = False):
+        self._h = None
+        devs = np.ascontiguousarray(list(devices), dtype=np.int32)
+        h = C.c_void_p()
+        check(lib.rbk_group_create(dim, ptr(devs), devs.shape[0], capacity_hint, 1 if keep_f64 else 0, C.byref(h)))
+        self._h = h
+        self.dim = dim
+        self.devices = [int(d) for d in devs]
+        self.device = self.devices[0]
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib.rbk_group_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _append(self, fn, rows: np.ndarray) -> int:
+        if rows.ndim != 2 or rows.shape[1] != self.dim:
+            raise DimensionError(RBK_EDIM, "Vectors must have the same length")
+        first = C.c_int64(-1)
+        check(fn(self._h, ptr(rows), rows.shape[0], C.byref(first)))
+        return first.value
+
+    def append_f64(self, rows) -> int:
+        return self._append(lib.rbk_group_append_f64, np.ascontiguousarray(rows, dtype=np.float64))
+
+    def append_f32(self, rows) -> int:
+        return self._append(lib.rbk_group_append_f32, np.ascontiguousarray(rows, dtype=np.float32))
+
+    def append_bf16(self, rows_u16) -> int:
+        return self._append(lib.rbk_group_append_bf16, np.ascontiguousarray(rows_u16, dtype=np.uint16))
+
+    def overwrite_f64_batch(self, slots, rows) -> None:
+        s = np.ascontiguousarray(slots, dtype=np.int64)
+        r = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, self.dim) if len(s) else np.zeros((0, self.dim))
+        if r.shape != (s.shape[0], self.dim):
+            raise DimensionError(RBK_EDIM, "Vectors must have the same length")
+        check(lib.rbk_group_overwrite_f64_batch(self._h, ptr(s), s.shape[0], ptr(r)))
+
+    def overwrite_f64(self, slot: int, row) -> None:
+        self.overwrite_f64_batch([slot], np.asarray(row, dtype=np.float64)[None, :])
+
+    def tombstone(self, slots) -> None:
+        s = np.ascontiguousarray(slots, dtype=np.int64)
+        check(lib.rbk_group_tombstone(self._h, ptr(s), s.shape[0]))
+
+    def clear(self) -> None:
+        check(lib.rbk_group_clear(self._h))
+
+    def count(self) -> int:
+        return lib.rbk_group_count(self._h)
+
+    def size(self) -> int:
+        return lib.rbk_group_size(self._h)
+
+    def search(self, queries, k_fetch: int, min_score: float | None = 0.5):
+        q = np.asarray(queries)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.dtype == np.float32:
+            q = np.ascontiguousarray(q)
+            fn = lib.rbk_group_search_f32
+        else:
+            q = np.ascontiguousarray(q, dtype=np.float64)
+            fn = lib.rbk_group_search_f64
+        B = q.shape[0]
+        slots = np.empty((B, k_fetch), dtype=np.int64)
+        scores = np.empty((B, k_fetch), dtype=np.float64)
+        counts = np.empty((B,), dtype=np.int32)
+        ms = C.c_float(0)
+        ms_arg = -np.inf if min_score is None else float(min_score)
+        check(fn(self._h, ptr(q), B, q.shape[1], k_fetch, ms_arg, ptr(slots), ptr(scores), ptr(counts), C.byref(ms)))
+        return slots, scores, counts, ms.value
+
+    def stats(self) -> dict:
+        out = {"devices": len(self.devices), "redone_batches": lib.rbk_group_redone_batches(self._h)}
+        per = []
+        for i in range(len(self.devices)):
+            st = RbkStats()
+            check(lib.rbk_index_stats(C.c_void_p(lib.rbk_group_member(self._h, i)), C.byref(st)))
+            per.append({f: getattr(st, f) for f, _ in RbkStats._fields_})
+        for k in ("searches", "queries", "fallback_queries", "scan_launches", "kernel_launches", "retry_batches"):
+            out[k] = sum(p[k] for p in per)
+        out["per_device"] = per
+        return out
 
 
 def merge_topk_device(device: int, stream: int, G: int, B: int, k_fetch: int, slots_ptr: int, scores_ptr: int,

@@ -13,16 +13,16 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "lib" / "librbk_knn.so"
-SOURCES = ["rbk_capi.cu", "rbk_scan.cu", "rbk_scan2.cu", "rbk_scan4.cu", "rbk_scan3.cu", "rbk_ingest.cu", "rbk_finalize.cu"]
+SOURCES = ["rbk_capi.cu", "rbk_group.cu", "rbk_scan.cu", "rbk_scan2.cu", "rbk_scan4.cu", "rbk_scan3.cu", "rbk_ingest.cu", "rbk_finalize.cu"]
 # RBK_EXPERIMENTAL=1 in the environment of the BUILD adds -DRBK_EXPERIMENTAL: the measured-and-rejected kernel
 # variants of DESIGN.md §7 and their A/B switches (rbk_scan3.cu is empty without it).  Never set for a release.
-HEADERS = ["rbk_internal.h", "rbk_ptx.cuh", "rbk_epilogue.cuh", "../../include/rbk_knn.h"]
+HEADERS = ["rbk_internal.h", "rbk_index_impl.h", "rbk_ptx.cuh", "rbk_epilogue.cuh", "../../include/rbk_knn.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",            # fp64 re-rank must never contract a*b+c (parity contract)
     "--extended-lambda",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "-ldl",
 ]
 
 

@@ -12,17 +12,15 @@
 #include <string>
 #include <vector>
 
-#include "../../include/rbk_knn.h"
-#include "rbk_internal.h"
+#include "rbk_index_impl.h"
 
 using namespace rbk;
 
-namespace {
-
-thread_local std::string g_err;
-
+namespace rbk {
+namespace impl {
+thread_local std::string g_err_storage;
 rbk_status fail(rbk_status st, const std::string& msg) {
-  g_err = msg;
+  g_err_storage = msg;
   return st;
 }
 rbk_status cuda_fail(cudaError_t e, const char* what) {
@@ -30,11 +28,13 @@ rbk_status cuda_fail(cudaError_t e, const char* what) {
   return fail(e == cudaErrorMemoryAllocation ? RBK_ENOMEM : RBK_ECUDA,
               std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
 }
-#define CK(expr)                                         \
-  do {                                                   \
-    cudaError_t _e = (expr);                             \
-    if (_e != cudaSuccess) return cuda_fail(_e, #expr);  \
-  } while (0)
+const char* last_error() { return g_err_storage.c_str(); }
+}  // namespace impl
+}  // namespace rbk
+using namespace rbk::impl;
+
+namespace {
+
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -80,115 +80,9 @@ rbk_status encode_rows_tmap(CUtensorMap* out, const void* base, int64_t rows, in
 
 int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
-template <typename T>
-struct DevBuf {
-  T* p = nullptr;
-  size_t n = 0;
-  cudaError_t ensure(size_t want) {
-    if (want <= n) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    n = 0;
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T));
-    if (e == cudaSuccess) n = want;
-    return e;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    n = 0;
-  }
-};
-template <typename T>
-struct PinBuf {
-  T* p = nullptr;
-  size_t n = 0;
-  cudaError_t ensure(size_t want) {
-    if (want <= n) return cudaSuccess;
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    n = 0;
-    cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&p), want * sizeof(T));
-    if (e == cudaSuccess) n = want;
-    return e;
-  }
-  void release() {
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    n = 0;
-  }
-};
-
 }  // namespace
 
-struct rbk_index {
-  int dim = 0, dpad = 0, device = 0, sm_count = 0, margin = 16;
-  int64_t cap = 0, n_rows = 0, n_live = 0, slot_base = 0;
-  uint16_t* rows = nullptr;
-  float* inv_norm = nullptr;  // padded to a multiple of kBlockN (+ one tile), NaN-filled
-  double* norm2 = nullptr;
-  double* rows_f64 = nullptr;   // optional exact-source sidecar [cap][dim] (RBK_INDEX_KEEP_F64)
-  bool keep_f64 = false;
-  unsigned int* dead_bits = nullptr;
-  int* d_counter = nullptr;   // [0] tombstone counter, [1] eps_c_max (float bits)
-  cudaStream_t own_stream = nullptr, stream = nullptr;
-  std::mutex mu;
-  // ingest staging
-  DevBuf<unsigned char> stage;
-  DevBuf<int64_t> d_slots;
-  // search scratch
-  DevBuf<unsigned char> q_raw;
-  DevBuf<uint16_t> q_bf16;
-  DevBuf<double> q_f64, q_norm2, q_eps;
-  DevBuf<float> q_inv_norm, thr_init;
-  DevBuf<unsigned long long> cand;
-  DevBuf<int> cand_cnt, flags, fail_list, o_counts, part_rows, part_cnt, maxbin, progress;
-  DevBuf<unsigned int> hist;
-  DevBuf<long long> o_slots;
-  DevBuf<double> o_scores, part_scores;
-  DevBuf<float> dbg;
-  DevBuf<unsigned char> o_block;
-  PinBuf<unsigned char> h_block;
-  PinBuf<int> h_flags, h_counts;
-  PinBuf<long long> h_slots;
-  PinBuf<double> h_scores;
-  PinBuf<float> h_f32;
-  CUtensorMap tmap_c, tmap_c_half, tmap_c_quarter, tmap_c_half32, tmap_c_pf, tmap_c_r32;
-  int cluster4 = 1;          // B > 128: clusters of two CTA pairs with one operand multicast (rbk_scan4.cu)
-  int perf_probe = 0;
-  int max_lead_tiles = kMaxLeadTiles;
-  int seed_tile = -1;        // -1 = by unit count; RBK_KNN_SEED_TILE=0|1 forces
-  int kprime_override = 0;   // > 0 while a batch is re-scanned with the widest candidate margin
-  bool retry_wide = true;    // RBK_KNN_RETRY_WIDE=0: failed proofs go straight to the exhaustive kernel
-  int epi_halves = 0;        // 0 = default (2); RBK_KNN_HALVES=1|2 forces
-  int hybrid_res_kb = -1, hybrid_slots = 8;   // -1: hybrid pair kernel off
-  bool use_ts = false;  // pair kernel with queries in TMEM (dim <= 768): correct but not yet faster
-  bool force_1cta = false, force_streamed = true;   // query-resident pair kernel: measured slower
-  int prefetch_tiles = 0;
-  const void* tmap_c_base = nullptr;
-  int64_t tmap_c_rows = -1;
-  std::vector<cudaEvent_t> ev;
-  // scan-kernel timing without a host sync per search: (start, stop) event pairs are resolved lazily
-  // (rbk_index_stats, or when the ring wraps) into stats.scan_ms_total / stats.scans_timed
-  static constexpr int kTimingRing = 64;
-  cudaEvent_t tev[kTimingRing][2] = {};
-  uint64_t tev_head = 0, tev_tail = 0;   // [tail, head) pending
-  float pending_scan_ms = 0.f;           // scan time of the search being assembled (resolved pairs only)
-  rbk_stats stats;
-};
-
 namespace {
-
-struct DeviceGuard {
-  int prev = -1;
-  explicit DeviceGuard(int dev) {
-    cudaGetDevice(&prev);
-    if (prev != dev) cudaSetDevice(dev);
-  }
-  ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
-  }
-};
 
 cudaEvent_t get_event(rbk_index* ix, size_t i) {
   while (ix->ev.size() <= i) {
@@ -359,6 +253,9 @@ rbk_status refresh_corpus_tmap(rbk_index* ix) {
   return RBK_OK;
 }
 
+}  // namespace
+namespace rbk {
+namespace impl {
 rbk_status ensure_query_scratch(rbk_index* ix, int B, int elem) {
   CK(ix->q_raw.ensure(static_cast<size_t>(B) * ix->dim * elem));
   CK(ix->q_bf16.ensure(static_cast<size_t>(B) * ix->dpad));
@@ -375,6 +272,9 @@ rbk_status ensure_query_scratch(rbk_index* ix, int B, int elem) {
   CK(ix->hist.ensure(static_cast<size_t>(kMaxSubBatch) * kHistBins + 2 * kMaxSubBatch + ix->sm_count + 8));
   return RBK_OK;
 }
+}  // namespace impl
+}  // namespace rbk
+namespace {
 
 QueryBuffers query_buffers(rbk_index* ix, int q0) {
   QueryBuffers qb;
@@ -417,18 +317,33 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
     const int QB = (Bs + block_m - 1) / block_m;
     const int units = pairs ? ix->sm_count / 2 : ix->sm_count;
     int R = std::max(1, std::min(units / QB, n_tiles));
-    // B > 128: clusters of two pairs, one operand of every k-block multicast (rbk_scan4.cu).  An even number of
-    // query blocks: the pairs of a cluster take different blocks and share the corpus tile; odd: same block,
-    // alternate tiles, shared query slab.
+    // B > 128: clusters of two pairs, one operand of every k-block multicast (rbk_scan4.cu) - the kernel whose
+    // tensor pipe runs at 97 % - on every SM that can host a 4-CTA cluster (33 clusters = 132 of the 148 SMs of a
+    // B200: GPCs whose SM count is not a multiple of 4 leave 2 over), and CONCURRENTLY the pair kernel
+    // (rbk_scan2.cu) on the SMs that cannot, over its own slice of the corpus.  An even number of query blocks:
+    // the pairs of a cluster take different blocks and share the corpus tile; odd: same block, alternate tiles,
+    // shared query slab.
     const bool aligned = pairs ? scan_smem_base_is_aligned() : false;
     const int max_cl = (pairs && ix->cluster4) ? scan4_max_clusters(aligned) : 0;
-    const bool use4 = max_cl > 0;
+    const bool use4 = max_cl > 0 && n_tiles >= 2;
     const bool share_c = use4 && (QB % 2) == 0;
-    int RC = 0;
+    int RC = 0, R4 = 0, R2 = 0, T2 = 0;   // cluster ranges; list units per query block of each kernel; tiles of the tail
     if (use4) {
       const int n_cols = share_c ? QB / 2 : QB;
-      RC = std::max(1, std::min(max_cl / n_cols, share_c ? n_tiles : (n_tiles + 1) / 2));
-      R = share_c ? RC : 2 * RC;
+      RC = std::max(1, std::min(max_cl / n_cols, share_c ? n_tiles : n_tiles / 2));
+      R4 = share_c ? RC : 2 * RC;
+      // the tail: pairs on the SMs left over, if the scan is long enough to be worth a second launch
+      const int spare_pairs = (ix->sm_count - 4 * RC * n_cols) / 2;
+      R2 = ix->tail_pairs >= 0 ? std::min(ix->tail_pairs, spare_pairs / QB) : spare_pairs / QB;
+      if (n_tiles < 16 * (R4 + R2)) R2 = 0;
+      if (R2 > 0) {
+        // a pair of the tail needs tail_rho x the time of a cluster pair per tile (no multicast: 82 % vs 97 % tensor
+        // duty): tiles in proportion to capacity, so that both launches finish together
+        const double cap4 = R4, cap2 = R2 / ix->tail_rho;
+        T2 = static_cast<int>(n_tiles * cap2 / (cap4 + cap2) + 0.5);
+        if (T2 < R2) R2 = T2 = 0;
+      }
+      R = R4 + R2;
     }
     CUtensorMap tmap_q, tmap_q64;
     st = encode_rows_tmap(&tmap_q, ix->q_bf16.p + static_cast<size_t>(q0) * ix->dpad, Bs, ix->dpad, kBlockM);
@@ -464,6 +379,11 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
     sp.R = R;
     sp.RC = RC;
     sp.n_tiles = n_tiles;
+    sp.tile_begin = 0;
+    sp.tile_count = n_tiles - T2;
+    sp.R_local = R;
+    sp.unit_base = 0;
+    sp.prog_base = 0;
     cudaEvent_t* tev = next_scan_events(ix);
     CK(cudaEventRecord(tev[0], ix->stream));
     sp.prefetch_tiles = ix->prefetch_tiles;
@@ -490,8 +410,25 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
     // histogram before ~k'/2 peers have seeded finds no threshold and floods its lists.
     sp.seed_tile = ix->seed_tile >= 0 ? ix->seed_tile : ((pairs && R * 2 * halves >= 4 * kprime) ? 1 : 0);
     if (use4) {
+      if (R2 > 0) CK(cudaEventRecord(ix->ev_fork, ix->stream));   // scratch zeroed, queries prepared
       CK(launch_scan4(tmap_q, tmap_q64, ix->tmap_c_half, ix->tmap_c_quarter, sp, share_c, aligned, ix->stream,
                       &ix->stats.last_ring_stages));
+      if (R2 > 0) {
+        // launched SECOND, on its own stream: the cluster kernel's CTAs are placed first, the tail's pairs land on
+        // the SMs no 4-CTA cluster fits on.  (Were they ever placed the other way round the result would still be
+        // right - the kernels only exchange lower bounds - just slower.)
+        ScanParams st2 = sp;
+        st2.tile_begin = n_tiles - T2;
+        st2.tile_count = T2;
+        st2.R_local = R2;
+        st2.unit_base = R4;
+        st2.prog_base = RC * (share_c ? QB / 2 : QB);
+        CK(cudaStreamWaitEvent(ix->side_stream, ix->ev_fork, 0));
+        CK(launch_scan2(tmap_q, ix->tmap_c_half, ix->tmap_c_half, st2, false, halves, ix->side_stream, nullptr));
+        CK(cudaEventRecord(ix->ev_join, ix->side_stream));
+        CK(cudaStreamWaitEvent(ix->stream, ix->ev_join, 0));
+        ix->stats.kernel_launches++;
+      }
     } else
 #ifdef RBK_EXPERIMENTAL
     if (pairs && !ts && ix->hybrid_res_kb >= 0)
@@ -529,7 +466,7 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
       fp.rows_f64 = ix->rows_f64;
       fp.row_norm2 = ix->norm2;
       fp.n_rows = ix->n_rows;
-      fp.slot_base = ix->slot_base;
+      fp.slot = ix->slot;
       fp.q = query_buffers(ix, q0);
       fp.out_slots = d_slots + static_cast<size_t>(q0) * k_fetch;
       fp.out_scores = d_scores + static_cast<size_t>(q0) * k_fetch;
@@ -563,7 +500,7 @@ rbk_status run_fallback(rbk_index* ix, const std::vector<int>& fails, int k_fetc
   ep.row_norm2 = ix->norm2;
   ep.dead_bits = ix->dead_bits;
   ep.n_rows = ix->n_rows;
-  ep.slot_base = ix->slot_base;
+  ep.slot = ix->slot;
   ep.q_f64 = ix->q_f64.p;
   ep.q_norm2 = ix->q_norm2.p;
   ep.part_scores = ix->part_scores.p;
@@ -580,6 +517,9 @@ rbk_status run_fallback(rbk_index* ix, const std::vector<int>& fails, int k_fetc
   return RBK_OK;
 }
 
+}  // namespace
+namespace rbk {
+namespace impl {
 rbk_status check_search_args(rbk_index* ix, int B, bool have_q, int query_dim, int k_fetch, double min_score) {
   if (!ix) return fail(RBK_EINVAL, "null index");
   if (B < 0 || (B > 0 && !have_q)) return fail(RBK_EINVAL, "bad queries argument");
@@ -588,15 +528,24 @@ rbk_status check_search_args(rbk_index* ix, int B, bool have_q, int query_dim, i
   if (min_score != min_score) return fail(RBK_EINVAL, "min_score is NaN");
   return RBK_OK;
 }
+}  // namespace impl
+}  // namespace rbk
+namespace {
 
 // Enqueue-only search of device-resident queries (caller holds the lock).  No host synchronisation: the
 // exactness flags land in d_flags and are the caller's to check (rbk_index_search_device_async).
+}  // namespace
+namespace rbk {
+namespace impl {
 rbk_status enqueue_search(rbk_index* ix, const void* d_q, int src_type, int B, int k_fetch, double min_score,
                           long long* d_slots, double* d_scores, int* d_counts, int* d_flags) {
   ix->stats.searches++;
   ix->stats.queries += B;
   return run_scan(ix, d_q, src_type, B, k_fetch, min_score, d_slots, d_scores, d_counts, d_flags, nullptr);
 }
+}  // namespace impl
+}  // namespace rbk
+namespace {
 
 // Whole search, synchronous.  q_host/q_dev: exactly one is non-null.  Host outputs (h_*) may be null
 // (device-output variant); device outputs may be null (host variant uses index scratch).
@@ -704,7 +653,7 @@ rbk_status search_core(rbk_index* ix, const void* q_host, const void* q_dev, int
 extern "C" {
 
 int rbk_abi_version(void) { return RBK_ABI_VERSION; }
-const char* rbk_last_error(void) { return g_err.c_str(); }
+const char* rbk_last_error(void) { return rbk::impl::last_error(); }
 
 rbk_status rbk_index_create(int32_t dim, int32_t device, int64_t capacity_hint, rbk_index** out) {
   return rbk_index_create_ex(dim, device, capacity_hint, 0, out);
@@ -737,6 +686,8 @@ rbk_status rbk_index_create_ex(int32_t dim, int32_t device, int64_t capacity_hin
   ix->stats.sm_count = ix->sm_count;
 #ifdef RBK_EXPERIMENTAL   // A/B switches of development builds; the shipped library reads no environment
   if (const char* m = getenv("RBK_KNN_CLUSTER4")) ix->cluster4 = atoi(m);
+  if (const char* m = getenv("RBK_KNN_TAIL_PAIRS")) ix->tail_pairs = atoi(m);
+  if (const char* m = getenv("RBK_KNN_TAIL_RHO")) ix->tail_rho = std::max(0.5, std::min(3.0, atof(m)));
   if (const char* m = getenv("RBK_KNN_MARGIN")) ix->margin = std::max(0, std::min(96, atoi(m)));
   if (const char* m = getenv("RBK_KNN_FORCE_1CTA")) ix->force_1cta = atoi(m) != 0;
   if (const char* m = getenv("RBK_KNN_RESIDENT")) ix->force_streamed = atoi(m) == 0;
@@ -756,6 +707,13 @@ rbk_status rbk_index_create_ex(int32_t dim, int32_t device, int64_t capacity_hin
     return cuda_fail(e, "cudaStreamCreate");
   }
   ix->stream = ix->own_stream;
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->side_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->ev_join, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    rbk_index_destroy(ix);
+    return cuda_fail(e, "cudaStreamCreate");
+  }
   e = cudaMalloc(reinterpret_cast<void**>(&ix->d_counter), 2 * sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(ix->d_counter, 0, 2 * sizeof(int));
   if (e != cudaSuccess) {
@@ -816,6 +774,12 @@ void rbk_index_destroy(rbk_index* ix) {
     for (auto& pr : ix->tev)
       for (cudaEvent_t e : pr)
         if (e) cudaEventDestroy(e);
+    if (ix->side_stream) {
+      cudaStreamSynchronize(ix->side_stream);
+      cudaStreamDestroy(ix->side_stream);
+    }
+    if (ix->ev_fork) cudaEventDestroy(ix->ev_fork);
+    if (ix->ev_join) cudaEventDestroy(ix->ev_join);
     if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
   }
   delete ix;
@@ -834,7 +798,7 @@ rbk_status rbk_index_set_slot_base(rbk_index* ix, int64_t slot_base) {
   if (!ix) return fail(RBK_EINVAL, "null index");
   if (slot_base < 0) return fail(RBK_EINVAL, "slot_base must be >= 0");
   std::lock_guard<std::mutex> lk(ix->mu);
-  ix->slot_base = slot_base;
+  ix->slot.base = slot_base;
   return RBK_OK;
 }
 

@@ -64,12 +64,14 @@ __device__ __forceinline__ void filter_init(FilterState& s, bool valid, float th
 // Raise thr from the global histogram (source 3).  Per-thread, no warp collectives.
 // Bins are fetched 16 at a time (four independent 16-byte L2 loads in flight): a dependent chain
 // of single loads cost ~0.7 us per 4 bins and made this function 23 % of the epilogue's time.
-static __device__ __noinline__ bool filter_refresh(FilterState& s, int kprime) {
-  if (!s.valid || (kExperimental && s.probe == 3)) return false;
-  const int mb = __ldcg(s.maxbin_q);
-  if (mb <= s.tb) return false;
-  const uint4* h4 = reinterpret_cast<const uint4*>(s.hist_q);
-  const int g_lo = (s.tb + 1) >> 2;   // lowest group that may hold a bin > tb
+// The walk is out of line (it is long and rare) and takes / returns SCALARS: handing it the FilterState by
+// reference forced the whole struct into local memory, and the hot loop then paid a local store per tile
+// (8.5 % of the warp samples of profiles/r01_scan_cfg3_final2.txt sat on `STL [R1+0x8]`).
+// Returns 0 if no bin edge with >= k' rows at or above it exists above bin `tb`; else (bin << 32) | raw-threshold bits.
+static __device__ __noinline__ unsigned long long histogram_walk(const unsigned int* hist_q, int mb, int tb, float qn,
+                                                                  int kprime) {
+  const uint4* h4 = reinterpret_cast<const uint4*>(hist_q);
+  const int g_lo = (tb + 1) >> 2;   // lowest group that may hold a bin > tb
   unsigned cum = 0;
   for (int g_hi = mb >> 2; g_hi >= g_lo; g_hi -= 4) {
     uint4 w[4];
@@ -82,18 +84,25 @@ static __device__ __noinline__ bool filter_refresh(FilterState& s, int kprime) {
 #pragma unroll
       for (int j = 3; j >= 0; --j) {
         const int b = g * 4 + j;
-        if (g >= g_lo && b <= mb && b > s.tb) {
+        if (g >= g_lo && b <= mb && b > tb) {
           cum += c[j];
-          if (cum >= static_cast<unsigned>(kprime)) {
-            s.tb = b;
-            s.thr = fmaxf(s.thr, bin_edge_raw(b, s.qn));
-            return true;
-          }
+          if (cum >= static_cast<unsigned>(kprime))
+            return (static_cast<unsigned long long>(b + 1) << 32) | __float_as_uint(bin_edge_raw(b, qn));
         }
       }
     }
   }
-  return false;
+  return 0ull;
+}
+__device__ __forceinline__ bool filter_refresh(FilterState& s, int kprime) {
+  if (!s.valid || (kExperimental && s.probe == 3)) return false;
+  const int mb = __ldcg(s.maxbin_q);
+  if (mb <= s.tb) return false;
+  const unsigned long long r = histogram_walk(s.hist_q, mb, s.tb, s.qn, kprime);
+  if (r == 0ull) return false;
+  s.tb = static_cast<int>(r >> 32) - 1;
+  s.thr = fmaxf(s.thr, __uint_as_float(static_cast<uint32_t>(r)));
+  return true;
 }
 
 // When to refresh: every tile while the threshold is still moving fast, then ever more rarely
@@ -236,8 +245,9 @@ __device__ __forceinline__ unsigned long long umin64(unsigned long long a, unsig
 
 // Warp-cooperative compaction of one list: bitonic sort of up to 256 keys (8 per lane,
 // element i = j*32 + lane), keep the best k', return the k'-th score (source 2).
-static __device__ __noinline__ void warp_compact(unsigned long long* list, int cnt, int kprime, int lane, float& new_thr,
-                                          int& new_cnt) {
+// Returns (bits of the k'-th score, or of -inf when the list is shorter) << 32 | entries kept - by value, so the
+// caller's filter state stays in registers.
+static __device__ __noinline__ unsigned long long warp_compact(unsigned long long* list, int cnt, int kprime, int lane) {
   constexpr uint32_t kFullMask = 0xFFFFFFFFu;
   unsigned long long k[8];
 #pragma unroll
@@ -286,9 +296,9 @@ static __device__ __noinline__ void warp_compact(unsigned long long* list, int c
   for (int j = 0; j < 8; ++j)
     if (j == (e >> 5)) sel = k[j];
   const unsigned long long kth = __shfl_sync(kFullMask, sel, e & 31);
-  new_thr = cnt >= kprime ? key_score(kth) : -INFINITY;
-  new_cnt = keep;
+  const float new_thr = cnt >= kprime ? key_score(kth) : -INFINITY;
   __syncwarp();
+  return (static_cast<unsigned long long>(__float_as_uint(new_thr)) << 32) | static_cast<unsigned>(keep);
 }
 
 // Warp-collective: compact every lane's list that could overflow on the next chunk.
@@ -303,12 +313,10 @@ __device__ __forceinline__ void filter_compact_if_needed(FilterState& s, int kpr
     unsigned long long* l = reinterpret_cast<unsigned long long*>(
         __shfl_sync(kFullMask, reinterpret_cast<unsigned long long>(s.list), src));
     const int c = __shfl_sync(kFullMask, s.cnt, src);
-    float nt;
-    int nc;
-    warp_compact(l, c, kprime, lane, nt, nc);
+    const unsigned long long r = warp_compact(l, c, kprime, lane);
     if (lane == src) {
-      s.thr = fmaxf(s.thr, nt);
-      s.cnt = nc;
+      s.thr = fmaxf(s.thr, __uint_as_float(static_cast<uint32_t>(r >> 32)));
+      s.cnt = static_cast<int>(static_cast<uint32_t>(r));
     }
   }
 }

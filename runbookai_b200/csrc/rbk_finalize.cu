@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p)
       rank += (sj > sc || (sj == sc && s_row[j] < row)) ? 1 : 0;
     }
     if (rank < p.k_fetch) {
-      p.out_slots[static_cast<size_t>(ql) * p.k_fetch + rank] = p.slot_base + row;
+      p.out_slots[static_cast<size_t>(ql) * p.k_fetch + rank] = p.slot.global(row);
       p.out_scores[static_cast<size_t>(ql) * p.k_fetch + rank] = sc;
     }
     if (rank == p.k_fetch - 1) s_ekth = sc;
@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(kExThreads) exact_merge_kernel(ExactParams p) 
   for (int i = tid; i < p.k_fetch; i += kExThreads) {
     const size_t o = static_cast<size_t>(q) * p.k_fetch + i;
     if (i < n) {
-      p.out_slots[o] = p.slot_base + t.row[i];
+      p.out_slots[o] = p.slot.global(t.row[i]);
       p.out_scores[o] = t.score[i];
     } else {
       p.out_slots[o] = -1;

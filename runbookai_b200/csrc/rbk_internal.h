@@ -55,6 +55,13 @@ struct ScanParams {
   int RC;       // cluster kernel: corpus ranges = clusters per column (R = RC when the pairs of a cluster share the
                 // corpus tile, 2 * RC when they share the query slab and alternate tiles)
   int n_tiles;  // ceil(n_rows / kBlockN)
+  // A scan may be split over two concurrent launches (the cluster kernel on the SMs that can host 4-CTA clusters, the
+  // pair kernel on the rest): each launch covers tiles [tile_begin, tile_begin + tile_count) with R_local ranges,
+  // its units are numbered unit_base.. inside the query block's R lists, its pacing slots start at prog_base.
+  int tile_begin, tile_count;
+  int R_local;   // corpus ranges of THIS launch (1-CTA / pair kernels; the cluster kernel uses RC)
+  int unit_base;
+  int prog_base;
 };
 
 cudaError_t launch_scan(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, const ScanParams& p,
@@ -116,6 +123,18 @@ struct QueryBuffers {
 cudaError_t launch_prep_queries(const void* src, int src_type, int B, int d, int dpad, double min_score,
                                 const float* eps_c, const QueryBuffers& qb, cudaStream_t stream);
 
+// local row -> global slot.  Contiguous shards: slot_base + row.  A group that deals rows out block-cyclically over
+// G devices (rbk_group.cu): device g's local row r is global slot ((r / block) * G + g) * block + r % block - still
+// monotonic in r, so per-shard lists stay sorted by global slot among equal scores.
+struct SlotLayout {
+  int64_t base = 0;
+  int32_t block = 0, G = 1, g = 0;   // block == 0: contiguous
+  __host__ __device__ int64_t global(int64_t row) const {
+    if (block == 0) return base + row;
+    return ((row / block) * G + g) * block + row % block;
+  }
+};
+
 struct FinalizeParams {
   const unsigned long long* cand;
   const int* cand_cnt;
@@ -128,7 +147,7 @@ struct FinalizeParams {
   const double* rows_f64;   // nullable: exact-source sidecar (pitch d); the re-rank reads it instead of `rows`
   const double* row_norm2;
   int64_t n_rows;
-  int64_t slot_base;
+  SlotLayout slot;
   QueryBuffers q;  // pointers already offset to the sub-batch
   long long* out_slots;   // [B][k_fetch]
   double* out_scores;     // [B][k_fetch]
@@ -147,7 +166,7 @@ struct ExactParams {
   const double* row_norm2;
   const unsigned int* dead_bits;  // tombstones
   int64_t n_rows;
-  int64_t slot_base;
+  SlotLayout slot;
   const double* q_f64;
   const double* q_norm2;
   double* part_scores;   // [n_fail][n_blocks][k_fetch]

@@ -51,8 +51,8 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   const int qb = blockIdx.x % p.QB;
   const int r = blockIdx.x / p.QB;
-  const int t0 = static_cast<int>(static_cast<long long>(p.n_tiles) * r / p.R);
-  const int t1 = static_cast<int>(static_cast<long long>(p.n_tiles) * (r + 1) / p.R);
+  const int t0 = p.tile_begin + static_cast<int>(static_cast<long long>(p.tile_count) * r / p.R_local);
+  const int t1 = p.tile_begin + static_cast<int>(static_cast<long long>(p.tile_count) * (r + 1) / p.R_local);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -78,7 +78,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp, elected issue) =====================
-    volatile int* prog = p.progress + r * p.QB;
+    volatile int* prog = p.progress + p.prog_base + r * p.QB;
     int s = 0;
     uint32_t ph = 0;
     for (int tile = t0; tile < t1; ++tile) {
@@ -128,7 +128,8 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue: thread <-> query =====================
-    run_epilogue<false>(p, tail->invc, tail->tmem_full, tail->tmem_empty, tmem_base, qb, r, 0u, t0, t1, warp, lane);
+    run_epilogue<false>(p, tail->invc, tail->tmem_full, tail->tmem_empty, tmem_base, qb, p.unit_base + r, 0u, t0, t1, warp,
+                        lane);
   }
 
   tc_fence_before();
@@ -149,7 +150,7 @@ cudaError_t launch_scan(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c, co
   // per-device attribute; cheap enough to set on every launch
   cudaError_t e = cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  scan_kernel<<<p.QB * p.R, kScanThreads, smem, stream>>>(tmap_q, tmap_c, p);
+  scan_kernel<<<p.QB * p.R_local, kScanThreads, smem, stream>>>(tmap_q, tmap_c, p);
   return cudaGetLastError();
 }
 

@@ -101,8 +101,8 @@ scan2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
   const int pair = blockIdx.x >> 1;
   const int qb = pair % p.QB;                        // 256-query block
   const int r = pair / p.QB;                         // corpus range
-  const int t0 = static_cast<int>(static_cast<long long>(p.n_tiles) * r / p.R);
-  const int t1 = static_cast<int>(static_cast<long long>(p.n_tiles) * (r + 1) / p.R);
+  const int t0 = p.tile_begin + static_cast<int>(static_cast<long long>(p.tile_count) * r / p.R_local);
+  const int t1 = p.tile_begin + static_cast<int>(static_cast<long long>(p.tile_count) * (r + 1) / p.R_local);
   const int q_row0 = qb * 2 * kBlockM + static_cast<int>(rank) * kBlockM;   // this CTA's first query
   // corpus k-steps per tile: streamed K=64 per stage, resident K=32 per stage
   const int n_ksteps = kRes ? (p.dpad + kKR - 1) / kKR : p.num_kb;
@@ -142,7 +142,7 @@ scan2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
       }
       __syncwarp();
     }
-    volatile int* prog = p.progress + r * p.QB;
+    volatile int* prog = p.progress + p.prog_base + r * p.QB;
     int s = 0;
     uint32_t ph = 0;
     for (int tile = t0; tile < t1; ++tile) {
@@ -229,8 +229,8 @@ scan2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     }
   } else {
     // ===================== epilogue: thread <-> query (both CTAs) =====================
-    run_epilogue<true, kHalves>(p, tail->invc, tail->tmem_full, tail->tmem_empty, tmem_base, qb, r, rank, t0, t1,
-                                     warp, lane);
+    run_epilogue<true, kHalves>(p, tail->invc, tail->tmem_full, tail->tmem_empty, tmem_base, qb, p.unit_base + r, rank,
+                                t0, t1, warp, lane);
   }
 
   tc_fence_before();
@@ -309,8 +309,8 @@ scan2h_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   const int pair = blockIdx.x >> 1;
   const int qb = pair % p.QB;
   const int r = pair / p.QB;
-  const int t0 = static_cast<int>(static_cast<long long>(p.n_tiles) * r / p.R);
-  const int t1 = static_cast<int>(static_cast<long long>(p.n_tiles) * (r + 1) / p.R);
+  const int t0 = p.tile_begin + static_cast<int>(static_cast<long long>(p.tile_count) * r / p.R_local);
+  const int t1 = p.tile_begin + static_cast<int>(static_cast<long long>(p.tile_count) * (r + 1) / p.R_local);
   const int q_row0 = qb * 2 * kBlockM + static_cast<int>(rank) * kBlockM;
 
   if (warp == 0 && lane == 0) {
@@ -347,7 +347,7 @@ scan2h_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       }
       __syncwarp();
     }
-    volatile int* prog = p.progress + r * p.QB;
+    volatile int* prog = p.progress + p.prog_base + r * p.QB;
     int s = 0;
     uint32_t ph = 0;
     for (int tile = t0; tile < t1; ++tile) {
@@ -416,7 +416,8 @@ scan2h_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       }
     }
   } else {
-    run_epilogue<true>(p, tail->invc, tail->tmem_full, tail->tmem_empty, tmem_base, qb, r, rank, t0, t1, warp, lane);
+    run_epilogue<true>(p, tail->invc, tail->tmem_full, tail->tmem_empty, tmem_base, qb, p.unit_base + r, rank, t0, t1, warp,
+                       lane);
   }
 
   tc_fence_before();
@@ -451,7 +452,7 @@ static cudaError_t launch_scan2_t(const CUtensorMap& tmap_q, const CUtensorMap& 
   cudaError_t e = cudaFuncSetAttribute(scan2_kernel<kRes, kHalves>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  scan2_kernel<kRes, kHalves><<<2 * p.QB * p.R, 64 + 128 * kHalves, smem, stream>>>(tmap_q, tmap_c, tmap_pf, p, n_stages);
+  scan2_kernel<kRes, kHalves><<<2 * p.QB * p.R_local, 64 + 128 * kHalves, smem, stream>>>(tmap_q, tmap_c, tmap_pf, p, n_stages);
   return cudaGetLastError();
 }
 
@@ -493,7 +494,7 @@ cudaError_t launch_scan2h(const CUtensorMap& tmap_q, const CUtensorMap& tmap_c_h
   const size_t smem = static_cast<size_t>(res_kb + n_slots) * kPanelBytes + sizeof(SmemTailH);
   cudaError_t e = cudaFuncSetAttribute(scan2h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  scan2h_kernel<<<2 * p.QB * p.R, kScanThreads, smem, stream>>>(tmap_q, tmap_c_half, p, res_kb, n_slots);
+  scan2h_kernel<<<2 * p.QB * p.R_local, kScanThreads, smem, stream>>>(tmap_q, tmap_c_half, p, res_kb, n_slots);
   return cudaGetLastError();
 }
 

@@ -93,8 +93,8 @@ scan3_kernel(const __grid_constant__ CUtensorMap tmap_c, const ScanParams p, con
   const int pair = blockIdx.x >> 1;
   const int qb = pair % p.QB;
   const int r = pair / p.QB;
-  const int t0 = static_cast<int>(static_cast<long long>(p.n_tiles) * r / p.R);
-  const int t1 = static_cast<int>(static_cast<long long>(p.n_tiles) * (r + 1) / p.R);
+  const int t0 = static_cast<int>(static_cast<long long>(p.n_tiles) * r / p.R_local);
+  const int t1 = static_cast<int>(static_cast<long long>(p.n_tiles) * (r + 1) / p.R_local);
   const int n_stages_per_sub = p.num_kb / kKbPerStage;   // host guarantees num_kb % kKbPerStage == 0
   constexpr int kSubPerTile = kBlockN / kSubN;           // 4
 

@@ -76,13 +76,13 @@ scan4_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_constan
   const int col = cl % n_cols;
   const int rc = cl / n_cols;                        // corpus range of this cluster
   const int qb = kShareC ? 2 * col + pr : col;       // 256-query block of this pair
-  const int t0 = static_cast<int>(static_cast<long long>(p.n_tiles) * rc / p.RC);
-  const int t1 = static_cast<int>(static_cast<long long>(p.n_tiles) * (rc + 1) / p.RC);
+  const int t0 = p.tile_begin + static_cast<int>(static_cast<long long>(p.tile_count) * rc / p.RC);
+  const int t1 = p.tile_begin + static_cast<int>(static_cast<long long>(p.tile_count) * (rc + 1) / p.RC);
   // this pair's tiles: t_first, t_first + t_step, ... (n_iter of them; indices >= t1 are phantoms)
   const int t_step = kShareC ? 1 : 2;
   const int t_first = kShareC ? t0 : t0 + pr;
   const int n_iter = kShareC ? t1 - t0 : (t1 - t0 + 1) / 2;
-  const int unit = kShareC ? rc : 2 * rc + pr;       // list / publisher index inside the query block (p.R of them)
+  const int unit = p.unit_base + (kShareC ? rc : 2 * rc + pr);       // list / publisher index inside the query block (p.R of them)
   const uint16_t mc_mask = static_cast<uint16_t>(0x5u << c);              // same-parity CTA of both pairs
   const uint16_t pair_mask = static_cast<uint16_t>(0x3u << (2 * pr));
 
@@ -112,7 +112,7 @@ scan4_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp, elected issue; all four CTAs) =====================
-    volatile int* prog = p.progress + rc * n_cols;
+    volatile int* prog = p.progress + p.prog_base + rc * n_cols;
     const int q_row0 = qb * 2 * kBlockM + c * kBlockM;   // this CTA's first query
     int s = 0;
     uint32_t ph = 0;

@@ -156,6 +156,56 @@ def test_multi_device_index_single_process(rb, oracle_mod):
         assert ix.count() == n - 500 and ix.stats()["devices"] == 2
 
 
+def test_group_one_handle_many_gpus_matches_oracle(rb, oracle_mod):
+    """rbk_group_*: the in-library multi-GPU index (one host process, one call per search: per-GPU scans, ONE
+    ncclAllGather of the packed blocks, merge kernel, one synchronisation).  Two GPUs when the box has them (NCCL
+    path), else a one-GPU group (same code minus the collective).  Rows are dealt out in 4096-row blocks, so appends
+    straddle blocks and devices; ties across devices, tombstones, bulk overwrite and the dirty-flag re-answer path
+    (a tie group larger than any candidate margin) are all checked against the oracle on the whole corpus."""
+    import torch
+    from runbookai_b200 import Group, synth
+    n, d = 30_000, 256
+    corpus = synth.random_corpus(n, d, 141)
+    q = synth.random_queries(9, d, 142)
+    synth.plant_neighbours(corpus, q, 12, 143)
+    corpus[4096 + 7] = corpus[5]                           # exact tie across the first block boundary (= across devices)
+    corpus[3 * 4096 + 1] = corpus[5]
+    devs = [0, 1] if torch.cuda.device_count() > 1 else [0]
+    with Group(d, devs) as g:
+        for r0 in range(0, n, 7000):                       # appends that straddle blocks and devices
+            assert g.append_bf16(corpus[r0:r0 + 7000]) == r0
+        assert g.size() == n and g.count() == n
+        check_against_oracle(oracle_mod, g, corpus, q, 24, 0.5)
+        check_against_oracle(oracle_mod, g, corpus, q, 24, None)
+        check_against_oracle(oracle_mod, g, corpus, q.astype(np.float64), 112, None)
+        dead = np.random.default_rng(144).choice(n, 500, replace=False)
+        g.tombstone(dead)
+        live = np.ones(n, dtype=np.uint8)
+        live[dead] = 0
+        check_against_oracle(oracle_mod, g, corpus, q, 24, None, live=live)
+        slots = np.flatnonzero(live)[::37][:300]
+        new = synth.bf16_bits_to_f32(synth.random_corpus(len(slots), d, 145)).astype(np.float64)
+        g.overwrite_f64_batch(slots, new)
+        corpus[slots] = synth.f32_to_bf16_bits(new.astype(np.float32))
+        check_against_oracle(oracle_mod, g, corpus, q, 24, 0.5, live=live)
+        assert g.count() == n - 500 and g.stats()["devices"] == len(devs) and g.stats()["redone_batches"] == 0
+        # 150 duplicates of one row, all alive: no margin holds the tie group -> a shard's proof fails, the flag
+        # travels through the all-gather + merge, the batch is re-answered (wide rescan / exhaustive) and still exact
+        dup = np.flatnonzero(live)[100:250]
+        rowv = (q[0] * 0.5).astype(np.float64)
+        g.overwrite_f64_batch(dup, np.tile(rowv, (150, 1)))
+        corpus[dup] = synth.f32_to_bf16_bits(rowv.astype(np.float32))
+        s_, v_, c_ = check_against_oracle(oracle_mod, g, corpus, q, 20, 0.5, live=live)
+        assert s_[0, :20].tolist() == sorted(dup.tolist())[:20]
+        assert g.stats()["redone_batches"] >= 1
+        with pytest.raises(rb.DimensionError, match="Vectors must have the same length"):
+            g.search(np.ones((1, d + 1)), 4, 0.5)
+        g.clear()
+        assert g.size() == 0 and g.search(q, 5, None)[2].sum() == 0
+        assert g.append_bf16(corpus[:5000]) == 0
+        check_against_oracle(oracle_mod, g, corpus[:5000], q, 5, None)
+
+
 def test_input_formats_agree_and_rows_read_back(rb, oracle_mod):
     from runbookai_b200 import synth
     n, d = 3000, 96
