@@ -317,14 +317,18 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
     const int QB = (Bs + block_m - 1) / block_m;
     const int units = pairs ? ix->sm_count / 2 : ix->sm_count;
     int R = std::max(1, std::min(units / QB, n_tiles));
-    // B > 128: clusters of two pairs, one operand of every k-block multicast (rbk_scan4.cu) - the kernel whose
-    // tensor pipe runs at 97 % - on every SM that can host a 4-CTA cluster (33 clusters = 132 of the 148 SMs of a
-    // B200: GPCs whose SM count is not a multiple of 4 leave 2 over), and CONCURRENTLY the pair kernel
-    // (rbk_scan2.cu) on the SMs that cannot, over its own slice of the corpus.  An even number of query blocks:
-    // the pairs of a cluster take different blocks and share the corpus tile; odd: same block, alternate tiles,
-    // shared query slab.
+    // EXPERIMENTAL builds only (RBK_KNN_CLUSTER4=1): clusters of two pairs, one operand of every k-block multicast
+    // (rbk_scan4.cu) - the kernel whose tensor pipe runs at 97 % - on every SM that can host a 4-CTA cluster (33
+    // clusters = 132 of the 148 SMs of a B200), and CONCURRENTLY the pair kernel (rbk_scan2.cu) on the SMs that
+    // cannot, over its own slice of the corpus.  Measured within 2 % of the pair kernel alone (power-bound), so the
+    // default build launches the pair kernel on all SMs.  An even number of query blocks: the pairs of a cluster
+    // take different blocks and share the corpus tile; odd: same block, alternate tiles, shared query slab.
+#ifdef RBK_EXPERIMENTAL
     const bool aligned = pairs ? scan_smem_base_is_aligned() : false;
     const int max_cl = (pairs && ix->cluster4) ? scan4_max_clusters(aligned) : 0;
+#else
+    const int max_cl = 0;
+#endif
     const bool use4 = max_cl > 0 && n_tiles >= 2;
     const bool share_c = use4 && (QB % 2) == 0;
     int RC = 0, R4 = 0, R2 = 0, T2 = 0;   // cluster ranges; list units per query block of each kernel; tiles of the tail
@@ -348,7 +352,7 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
     CUtensorMap tmap_q, tmap_q64;
     st = encode_rows_tmap(&tmap_q, ix->q_bf16.p + static_cast<size_t>(q0) * ix->dpad, Bs, ix->dpad, kBlockM);
     if (st != RBK_OK) return st;
-    if (use4) {
+    if (use4) {   // (never in the default build)
       st = encode_rows_tmap(&tmap_q64, ix->q_bf16.p + static_cast<size_t>(q0) * ix->dpad, Bs, ix->dpad, kBlockM / 2);
       if (st != RBK_OK) return st;
     }
@@ -409,6 +413,7 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
     // 0.07 ms at 65k rows): with one or two tiles per unit and only two seeds from each, a unit that reads the
     // histogram before ~k'/2 peers have seeded finds no threshold and floods its lists.
     sp.seed_tile = ix->seed_tile >= 0 ? ix->seed_tile : ((pairs && R * 2 * halves >= 4 * kprime) ? 1 : 0);
+#ifdef RBK_EXPERIMENTAL
     if (use4) {
       if (R2 > 0) CK(cudaEventRecord(ix->ev_fork, ix->stream));   // scratch zeroed, queries prepared
       CK(launch_scan4(tmap_q, tmap_q64, ix->tmap_c_half, ix->tmap_c_quarter, sp, share_c, aligned, ix->stream,
@@ -429,9 +434,7 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
         CK(cudaStreamWaitEvent(ix->stream, ix->ev_join, 0));
         ix->stats.kernel_launches++;
       }
-    } else
-#ifdef RBK_EXPERIMENTAL
-    if (pairs && !ts && ix->hybrid_res_kb >= 0)
+    } else if (pairs && !ts && ix->hybrid_res_kb >= 0)
       CK(launch_scan2h(tmap_q, ix->tmap_c_half, sp, ix->hybrid_res_kb, ix->hybrid_slots, ix->stream));
     else if (ts)
       CK(launch_scan3(ix->tmap_c_r32, sp, ix->q_bf16.p + static_cast<size_t>(q0) * ix->dpad, ix->stream));

@@ -107,7 +107,7 @@ struct rbk_index {
   rbk::impl::PinBuf<double> h_scores;
   rbk::impl::PinBuf<float> h_f32;
   CUtensorMap tmap_c, tmap_c_half, tmap_c_quarter, tmap_c_half32, tmap_c_pf, tmap_c_r32;
-  int cluster4 = 1;          // B > 128: clusters of two CTA pairs with one operand multicast (rbk_scan4.cu)
+  int cluster4 = 0;          // EXPERIMENTAL builds: clusters of two CTA pairs with one operand multicast (rbk_scan4.cu)
   int tail_pairs = -1;       // pairs per query block of the concurrent pair-kernel tail (-1 = every spare SM pair)
   double tail_rho = 1.15;    // per-tile time of a tail pair relative to a cluster pair (split of the corpus)
   cudaStream_t side_stream = nullptr;   // the tail's stream, forked from / joined to `stream` with events

@@ -1,12 +1,17 @@
 // rbk_scan4.cu — K1 for batches of more than 128 queries on CLUSTERS OF TWO CTA PAIRS (4 CTAs) with one
 // operand of every k-block delivered by TMA MULTICAST.
 //
-// Why.  The pair kernel (rbk_scan2.cu) is bound by the L2 slices' output bandwidth, not by the tensor pipe or
-// HBM: every pair pulls (256 + 256) x 768 x 2 B = 786 KB through the L2->SM fabric per 256 x 256 tile
-// (128 flop per byte), ncu shows that fabric at ~10.6 TB/s in every variant and clock state, the tensor pipe at
-// 76 % (profiles/r01_scan_cfg3_final2.txt) - and the same 2x-the-corpus traffic caps the B=256 shapes at ~75 % of
-// the HBM roof.  Two pairs that need the SAME operand slab can have it read from L2 once and written into both
-// pairs' shared memory by one multicast TMA: 590 KB per pair-tile instead of 786 KB (-25 %).
+// Why it was built, and what it measured (round 2).  Every pair of the pair kernel (rbk_scan2.cu) pulls
+// (256 + 256) x 768 x 2 B = 786 KB through the L2->SM fabric per 256 x 256 tile and its tensor pipe is busy 82 % of
+// the SM's active cycles (profiles/r01_scan_cfg3_final2.txt).  Two pairs that need the SAME operand slab can have it
+// read from L2 once and written into both pairs' shared memory by one multicast TMA: 590 KB of L2 reads per
+// pair-tile instead of 786 KB.  Result on B200 (profiles/r02_scan4_cfg3_128sm.txt): L2 slice traffic -22 %, tensor
+// pipe 96.7 % of active cycles - but only 33 clusters of 4 CTAs fit the chip (GPCs whose SM count is not a
+// multiple of 4 leave SMs over; scripts/probes/cluster_probe.cu), i.e. 128-132 of 148 SMs, and under the 1 kW power
+// cap every variant - pair kernel on 144 SMs, this kernel on 128, this kernel plus a concurrent pair-kernel tail on
+// the spare SMs (rbk_capi.cu, run_scan) - lands within 2 % of the others (profiles/r02_ab_cluster_multicast_*.jsonl:
+// cfg3 10.95-11.15 ms, cfg2 0.286 ms, cfg5 1.49-1.51 ms, cfg4 shard 4.35-4.45 ms on one box).  The long scans are
+// bound by power, not by the fabric, so the simpler kernel ships and this one stays behind -DRBK_EXPERIMENTAL.
 //
 // Two sharing modes, chosen per launch:
 //   kShareC  (even number of 256-query blocks): the pairs of a cluster hold DIFFERENT query blocks and walk the
@@ -24,6 +29,7 @@
 //     only when both pairs' MMAs have consumed it: each leader's tcgen05.commit is multicast to all four CTAs;
 //   * tmem_full / tmem_empty stay inside a pair (commit mask = the pair's two ranks), as in rbk_scan2.cu.
 // The two pairs therefore advance in lockstep at smem-stage granularity, by construction.
+#ifdef RBK_EXPERIMENTAL   // measured (profiles/r02_scan4_cfg3_128sm.txt, r02_ab_cluster_multicast_*.jsonl): not in the default build
 #include "rbk_epilogue.cuh"
 #include "rbk_internal.h"
 #include "rbk_ptx.cuh"
@@ -253,3 +259,5 @@ cudaError_t launch_scan4(const CUtensorMap& tmap_q128, const CUtensorMap& tmap_q
 }
 
 }  // namespace rbk
+
+#endif  // RBK_EXPERIMENTAL

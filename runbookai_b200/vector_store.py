@@ -19,12 +19,21 @@ create_vector_store) keeps ONE device index and slot table per (real path of the
 process, reference-counted: the first opener loads it, later openers attach in O(1), the last close()
 frees it.  Instances sharing an index see each other's mutations at once (the reference's copies only
 converge at the next reload); each instance still owns its SQLite connection.
+
+Reload sidecar.  The reference re-parses every BLOB of the table at every construction
+(vector-store.ts:56-66).  Next to `<db>` this mirror keeps `<db>.rbk`: the same float64 rows in rowid order as ONE
+contiguous little-endian matrix plus the id table, stamped with a fingerprint of the table (row count and highest
+rowid - every mutation the reference's code can make, INSERT OR REPLACE / DELETE, moves one of the two).  A matching
+sidecar is memory-mapped and handed to `rbk_index_append_f64` in 64 MB slices: no SQL scan of the BLOBs, no per-row
+Python, no intermediate copy.  A missing or stale sidecar falls back to the BLOBs (the source of truth) and is
+rewritten at close().  RUNBOOK_KNN_SIDECAR=0 turns it off.
 """
 from __future__ import annotations
 
 import json
 import os
 import sqlite3
+import struct
 import threading
 from dataclasses import asdict, dataclass, field
 from typing import Sequence
@@ -51,6 +60,8 @@ SCHEMA = """
       CREATE INDEX IF NOT EXISTS idx_vector_type ON vector_embeddings(type);
 """
 NOT_CONFIGURED = "Embedder not configured. Set OPENAI_API_KEY."
+SIDECAR_MAGIC = b"RBKVEC1\0"
+_SIDECAR_HDR = struct.Struct("<8sIIQQQQ")   # magic, version, dim, rows, table count, max rowid, bytes of the id table
 
 
 @dataclass
@@ -120,6 +131,10 @@ class VectorStore:
         self._db_lock = threading.RLock()
         self.device = int(os.environ.get("RUNBOOK_KNN_DEVICE", "0")) if device is None else device
         self._closed = False
+        self._db_path = db_path
+        self._sidecar = (db_path != ":memory:" and not db_path.startswith("file:")
+                         and os.environ.get("RUNBOOK_KNN_SIDECAR", "1") != "0")
+        self.loaded_from_sidecar = False
         self._init_schema()
         if shared and db_path != ":memory:" and not db_path.startswith("file:"):
             key = (os.path.realpath(db_path), self.device)
@@ -189,8 +204,103 @@ class VectorStore:
             self._index = self._index_factory(dim, self.device)
         return self._index
 
+    # ------------------------------------------------------------------ reload sidecar
+    def _fingerprint(self) -> tuple[int, int]:
+        r = self.db.execute("SELECT COUNT(*), COALESCE(MAX(rowid), 0) FROM vector_embeddings").fetchone()
+        return int(r[0]), int(r[1])
+
+    def _load_sidecar(self) -> bool:
+        """Bulk-load from `<db>.rbk` if it describes the table as it is now."""
+        path = self._db_path + ".rbk"
+        try:
+            with open(path, "rb") as f:
+                hdr = f.read(_SIDECAR_HDR.size)
+                if len(hdr) != _SIDECAR_HDR.size:
+                    return False
+                magic, ver, dim, n, count, max_rowid, id_bytes = _SIDECAR_HDR.unpack(hdr)
+                if magic != SIDECAR_MAGIC or ver != 1 or (count, max_rowid) != self._fingerprint() or n != count:
+                    return False
+                off = (_SIDECAR_HDR.size + id_bytes + 63) // 64 * 64
+                if os.path.getsize(path) != off + n * dim * 8:
+                    return False
+                ids = f.read(id_bytes).decode("utf-8").split("\n") if n else []
+            if len(ids) != n:
+                return False
+            if n == 0:
+                return True
+            mm = np.memmap(path, dtype="<f8", mode="r", offset=off, shape=(n, dim))
+            ix = self._ensure_index(dim)
+            step = max(1, (64 << 20) // (dim * 8))
+            for r0 in range(0, n, step):
+                first = ix.append_f64(mm[r0:r0 + step])          # straight from the page cache to the device
+                if first != r0:
+                    raise RuntimeError("slot numbering out of step while loading the sidecar")
+            for i, vid in enumerate(ids):
+                self._slot_of[vid] = i
+                self._ids.append(vid)
+            del mm
+            self.loaded_from_sidecar = True
+            return True
+        except (OSError, ValueError, UnicodeDecodeError):
+            return False
+
+    def save_sidecar(self) -> bool:
+        """Write `<db>.rbk` for the table as it is now (called by close() when missing or stale).  Rows of differing
+        length (S2) cannot be one matrix: no sidecar then."""
+        if not self._sidecar:
+            return False
+        with self._db_lock:
+            count, max_rowid = self._fingerprint()
+            cur = self.db.execute("SELECT id, embedding FROM vector_embeddings ORDER BY rowid")
+            first = cur.fetchone()
+            dim = len(first["embedding"]) // 8 if first else 0
+            tmp = self._db_path + ".rbk.tmp"
+            with open(tmp, "wb") as f:
+                rows = ([first] if first else [])
+                id_list = []
+                # the matrix offset depends on the size of the id table, which is only known after the scan: stream
+                # the BLOBs to a scratch file once, then write header + ids and append the scratch file
+                blobs_path = tmp + ".rows"
+                with open(blobs_path, "wb") as bf:
+                    while rows:
+                        for r in rows:
+                            if len(r["embedding"]) != dim * 8 or "\n" in r["id"]:
+                                bf.close()
+                                os.remove(blobs_path)
+                                f.close()
+                                os.remove(tmp)
+                                return False
+                            id_list.append(r["id"])
+                            bf.write(r["embedding"])
+                        rows = cur.fetchmany(4096)
+                idb = "\n".join(id_list).encode("utf-8")
+                f.seek(0)
+                f.write(_SIDECAR_HDR.pack(SIDECAR_MAGIC, 1, dim, len(id_list), count, max_rowid, len(idb)))
+                f.write(idb)
+                f.write(b"\0" * ((_SIDECAR_HDR.size + len(idb) + 63) // 64 * 64 - _SIDECAR_HDR.size - len(idb)))
+                with open(blobs_path, "rb") as bf:
+                    while True:
+                        buf = bf.read(64 << 20)
+                        if not buf:
+                            break
+                        f.write(buf)
+                os.remove(blobs_path)
+            os.replace(tmp, self._db_path + ".rbk")
+        return True
+
+    def _sidecar_is_current(self) -> bool:
+        try:
+            with open(self._db_path + ".rbk", "rb") as f:
+                hdr = f.read(_SIDECAR_HDR.size)
+            magic, ver, _, _, count, max_rowid, _ = _SIDECAR_HDR.unpack(hdr)
+            return magic == SIDECAR_MAGIC and ver == 1 and (count, max_rowid) == self._fingerprint()
+        except (OSError, struct.error):
+            return False
+
     def _load_embeddings(self) -> None:
         """vector-store.ts:56-66: every row, in rowid order, into the (device) index."""
+        if self._sidecar and self._load_sidecar():
+            return
         rows = self.db.execute("SELECT id, embedding FROM vector_embeddings").fetchall()
         if not rows:
             return
@@ -335,6 +445,12 @@ class VectorStore:
         if self._closed:
             return
         self._closed = True
+        if self._sidecar:
+            try:
+                if not self._sidecar_is_current():
+                    self.save_sidecar()
+            except (OSError, sqlite3.Error):
+                pass                      # the sidecar is an accelerator, never a reason to fail a close()
         self.db.close()
         st = self._st
         if st.key is not None:

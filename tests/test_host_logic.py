@@ -1,4 +1,5 @@
 """CPU suite, part 2: host logic and the C-ABI surface (no compute calls without a GPU)."""
+import os
 import ctypes
 import json
 import re
@@ -407,3 +408,47 @@ def test_micro_batcher_close_fails_queued_requests_and_rejects_new_ones(store):
     mb.close()
     with pytest.raises(RuntimeError, match="batcher closed"):
         fut.result(timeout=1)
+
+
+def test_reload_sidecar_is_used_when_current_and_ignored_when_stale(tmp_path):
+    """`<db>.rbk` (one contiguous f64 matrix + id table, stamped with the table's row count and highest
+    rowid) replaces the per-BLOB reload of vector-store.ts:56-66; any mutation by code that does not know about it
+    (the reference itself: INSERT OR REPLACE / DELETE) makes it stale and the BLOBs are read again."""
+    import sqlite3
+    from runbookai_b200 import embedder
+    from runbookai_b200.vector_store import VectorStore
+    embedder.configure(HashEmbedder(64))
+    path = str(tmp_path / "vectors.db")
+    mk = lambda: VectorStore(path, index_factory=lambda d, dev: OracleIndex(d))
+    s = mk()
+    s.add_chunks(_chunks(6, "docA"))
+    s.add_chunks(_chunks(4, "docB", text="kubernetes pod crashloop oom"))
+    s.delete_document("docA")
+    s.add_chunks(_chunks(3, "docA"))                       # re-added ids get new rowids: reload order = rowid order
+    q = "redis connection pool exhausted"
+    want = s.search(q, {"minScore": 0.1})
+    s.close()
+    assert os.path.exists(path + ".rbk")
+    s2 = mk()
+    assert s2.loaded_from_sidecar and s2.search(q, {"minScore": 0.1}) == want and s2._index.size() == 7
+    assert [i for i in s2._ids] == [r[0] for r in s2.db.execute("SELECT id FROM vector_embeddings ORDER BY rowid")]
+    s2.close()
+    # the reference (or any foreign writer) changes the table: count / max rowid move -> sidecar ignored, then rewritten
+    db = sqlite3.connect(path)
+    db.execute("DELETE FROM vector_embeddings WHERE id = 'vec_docB_0'")
+    db.commit()
+    db.close()
+    s3 = mk()
+    assert not s3.loaded_from_sidecar and s3._index.size() == 6
+    s3.close()
+    s4 = mk()
+    assert s4.loaded_from_sidecar and s4._index.size() == 6
+    s4.close()
+    os.environ["RUNBOOK_KNN_SIDECAR"] = "0"
+    try:
+        s5 = mk()
+        assert not s5.loaded_from_sidecar and s5.search(q, {"minScore": 0.1})
+        s5.close()
+    finally:
+        del os.environ["RUNBOOK_KNN_SIDECAR"]
+    embedder.reset()
