@@ -89,7 +89,6 @@ struct rbk_group {
   DevBuf<unsigned char> out;     // device 0: slots | scores | counts | flags[B+1]
   PinBuf<unsigned char> h_out, h_q;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  int64_t dirty_seen = 0;
   int64_t redone_batches = 0;
 };
 
@@ -186,12 +185,10 @@ rbk_status group_search(rbk_group* g, const void* queries, int elem, int32_t B, 
     DeviceGuard dg(g->devices[0]);
     CK(g->h_q.ensure(q_bytes));
     CK(g->h_out.ensure(out_bytes));
-    const size_t had = g->out.n;
     CK(g->out.ensure(out_bytes));
-    if (g->out.n != had) {   // (re)allocated: the running dirty count starts from zero again
-      CK(cudaMemsetAsync(g->out.p, 0, g->out.n, g->parts[0]->stream));
-      g->dirty_seen = 0;
-    }
+    // the merge kernel ADDS the number of dirty queries to the word after the flags: start every search from zero
+    // (its position depends on B and k_fetch, so a running count across calls of different shapes would be garbage)
+    CK(cudaMemsetAsync(g->out.p + out_bytes - 4, 0, 4, g->parts[0]->stream));
   }
   memcpy(g->h_q.p, queries, q_bytes);   // pinned staging: the G H2D copies below run concurrently, one per PCIe link
   const int src_type = elem == 8 ? 0 : 1;
@@ -223,10 +220,9 @@ rbk_status group_search(rbk_group* g, const void* queries, int elem, int32_t B, 
   }
   int dirty_total = 0;
   memcpy(&dirty_total, g->h_out.p + out_bytes - 4, 4);
-  if (dirty_total != g->dirty_seen) {
+  if (dirty_total != 0) {
     // some shard could not prove a query (more near-ties than its candidate margin): every shard re-answers the
     // batch through the synchronous path (wide rescan, then the exhaustive fp64 kernel), and the exchange is redone
-    g->dirty_seen = dirty_total;
     g->redone_batches++;
     for (int d = 0; d < g->G; ++d) {
       unsigned char* l = g->dev[d].local.p;
@@ -241,8 +237,6 @@ rbk_status group_search(rbk_group* g, const void* queries, int elem, int32_t B, 
     CK(cudaMemcpyAsync(g->h_out.p, g->out.p, out_bytes, cudaMemcpyDeviceToHost, i0->stream));
     CK(cudaEventRecord(g->ev1, i0->stream));
     CK(cudaStreamSynchronize(i0->stream));
-    memcpy(&dirty_total, g->h_out.p + out_bytes - 4, 4);
-    g->dirty_seen = dirty_total;
   }
   if (ms_out) cudaEventElapsedTime(ms_out, g->ev0, g->ev1);
   memcpy(out_slots, g->h_out.p, nk * 8);

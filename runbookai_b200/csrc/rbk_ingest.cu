@@ -110,24 +110,6 @@ __device__ __forceinline__ double bf16_bits_to_f64(uint32_t h) {
   return static_cast<double>(__uint_as_float(h << 16));
 }
 
-// x*x of a bf16 value as the binary64 the reference's `b[i] * b[i]` produces (embedder.ts:180) - exactly.  The
-// product of two 8-bit significands has 16 bits, so it is exact in binary32 as well as in binary64: for the values
-// embeddings actually take (2^-60 <= |x| <= 2^60, or 0) it is formed with ONE fp32 multiply and widened with integer
-// shifts, instead of two F2F.F64 conversions and a DMUL per element on the (narrow) fp64 pipe; anything else (tiny,
-// huge, inf, NaN) takes the literal convert-and-multiply path.  Either way the result is the correctly rounded
-// (= exact) product, so norm2 stays bit-identical to the oracle's normB.
-__device__ __forceinline__ double bf16_square_f64(uint32_t h) {
-  const uint32_t e = (h >> 7) & 0xFFu;
-  if (e - 67u <= 120u) {                                   // 2^-60 <= |x| < 2^61: x*x is a normal fp32, no rounding
-    const float x = __uint_as_float(h << 16);
-    const uint32_t b = __float_as_uint(x * x);             // sign 0
-    return __hiloint2double(static_cast<int>((b >> 3) + 0x38000000u), static_cast<int>(b << 29));
-  }
-  if ((h & 0x7FFFu) == 0u) return 0.0;
-  const double x = static_cast<double>(__uint_as_float(h << 16));
-  return __dmul_rn(x, x);
-}
-
 // ---- K3b: per-row norms.  The accumulation ORDER is part of the parity contract (norm2 must be the reference's
 // normB, embedder.ts:180: index order, multiply then add), so each row is one sequential fp64 chain owned by one
 // thread - but the chain must not wait on memory, and the loads must be coalesced.  A block of kNormRows threads
@@ -169,8 +151,12 @@ __global__ void __launch_bounds__(kNormRows) row_norms_kernel(const uint16_t* __
   double acc = 0.0;
   const int n16 = dpad >> 3;                         // 16-byte pieces per row
   constexpr int kPieces = kNormChunk / 8;            // 16-byte pieces per row and chunk; = pieces per thread and chunk
-  // piece index i of a chunk -> (row i / len16, unit i % len16): consecutive lanes = consecutive units of a row.
-  // The NEXT chunk's pieces travel in registers while this chunk is walked, so HBM latency overlaps the chains.
+  // piece index i of a chunk -> (row i / len16, unit i % len16): consecutive lanes = consecutive units of a row;
+  // all of a thread's 16 loads are in flight before the first is stored.  (Tried and measured on B200, 4M x 768:
+  // keeping the NEXT chunk's pieces in registers while this one is walked - no change, the kernel is not waiting on
+  // memory; forming x*x with one fp32 multiply and widening it to binary64 with integer shifts instead of two F2F
+  // conversions and a DMUL - 50 % SLOWER, the per-element range check costs more issue slots than the fp64 pipe
+  // saves.  The sequential fp64 chain per row, which the parity contract imposes, is what bounds this kernel.)
   uint4 v[kPieces];
   auto load_chunk = [&](int c0) {
     const int len16 = n16 - c0 < kPieces ? n16 - c0 : kPieces;
@@ -185,9 +171,9 @@ __global__ void __launch_bounds__(kNormRows) row_norms_kernel(const uint16_t* __
       }
     }
   };
-  load_chunk(0);
   for (int c0 = 0; c0 < n16; c0 += kPieces) {
     const int len16 = n16 - c0 < kPieces ? n16 - c0 : kPieces;
+    load_chunk(c0);
 #pragma unroll
     for (int u = 0; u < kPieces; ++u) {
       const int i = tid + u * kNormRows;
@@ -197,7 +183,6 @@ __global__ void __launch_bounds__(kNormRows) row_norms_kernel(const uint16_t* __
       }
     }
     __syncthreads();
-    if (c0 + kPieces < n16) load_chunk(c0 + kPieces);
     if (my_row >= 0) {
       const uint4* mine = s_chunk + tid * kNormPitch16;
       for (int g = 0; g < len16; ++g) {   // pad columns are zero: adding 0*0 is exact
@@ -205,8 +190,10 @@ __global__ void __launch_bounds__(kNormRows) row_norms_kernel(const uint16_t* __
         const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          acc = __dadd_rn(acc, bf16_square_f64(w[j] & 0xFFFFu));
-          acc = __dadd_rn(acc, bf16_square_f64(w[j] >> 16));
+          const double lo = bf16_bits_to_f64(w[j] & 0xFFFFu);
+          const double hi = bf16_bits_to_f64(w[j] >> 16);
+          acc = __dadd_rn(acc, __dmul_rn(lo, lo));
+          acc = __dadd_rn(acc, __dmul_rn(hi, hi));
         }
       }
     }

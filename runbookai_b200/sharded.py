@@ -103,6 +103,7 @@ class ShardedSearcher:
             if cuda:
                 b["h_out"] = torch.zeros_like(out, device="cpu").pin_memory()
             self._bufs = {key: b}
+            self._dirty_seen = 0          # fresh (zeroed) buffers: the merge kernel's running count restarts
         return self._bufs[key]
 
     # ------------------------------------------------------------------ device-resident path
