@@ -18,14 +18,47 @@ export interface ScoredId {
   score: number;
 }
 
+/** RUNBOOK_KNN_DEVICES="0,1,2,3" shards the corpus over those GPUs behind one handle (rbk_group_*). */
+function devicesFromEnv(): number | number[] {
+  const many = process.env.RUNBOOK_KNN_DEVICES;
+  if (many) return many.split(',').map(Number);
+  return Number(process.env.RUNBOOK_KNN_DEVICE ?? 0);
+}
+
 export class GpuEmbeddingIndex {
   private index: any | null = null;
   private idOfSlot: (string | null)[] = [];
   private slotOfId = new Map<string, number>();
   private dim = 0;
-  private mixedLengths = false;
+  /** ids whose stored vector has another length: while one is in the Map the reference's search throws (S2) */
+  private badIds = new Set<string>();
 
-  constructor(private device = Number(process.env.RUNBOOK_KNN_DEVICE ?? 0)) {}
+  /**
+   * One device index per resolved db path in the process, reference-counted: the reference builds and closes a
+   * VectorStore per call site (hook-handlers.ts:329-337), which must not mean an upload per call.  `acquire`
+   * returns the shared instance (first caller loads it), `release` frees the device memory with the last user.
+   */
+  private static shared = new Map<string, { ix: GpuEmbeddingIndex; refs: number; loaded: boolean }>();
+  static acquire(dbPath: string): { ix: GpuEmbeddingIndex; needsLoad: boolean } {
+    let e = GpuEmbeddingIndex.shared.get(dbPath);
+    if (!e) {
+      e = { ix: new GpuEmbeddingIndex(), refs: 0, loaded: false };
+      GpuEmbeddingIndex.shared.set(dbPath, e);
+    }
+    e.refs++;
+    const needsLoad = !e.loaded;
+    e.loaded = true;
+    return { ix: e.ix, needsLoad };
+  }
+  static release(dbPath: string): void {
+    const e = GpuEmbeddingIndex.shared.get(dbPath);
+    if (e && --e.refs === 0) {
+      GpuEmbeddingIndex.shared.delete(dbPath);
+      e.ix.index = null; // the addon's finalizer destroys the rbk_index / rbk_group
+    }
+  }
+
+  constructor(private device: number | number[] = devicesFromEnv()) {}
 
   get size(): number {
     return this.slotOfId.size;
@@ -36,13 +69,10 @@ export class GpuEmbeddingIndex {
     if (rows.length === 0) return;
     this.dim = rows[0].embedding.length / 8;
     const usable = rows.filter((r) => r.embedding.length === this.dim * 8);
-    this.mixedLengths = usable.length !== rows.length;
+    for (const r of rows) if (r.embedding.length !== this.dim * 8) this.badIds.add(r.id);
     this.index = new RbkIndex(this.dim, this.device, usable.length);
-    const packed = new Float64Array(usable.length * this.dim);
-    usable.forEach((r, i) => {
-      packed.set(new Float64Array(r.embedding.buffer, r.embedding.byteOffset, this.dim), i * this.dim);
-    });
-    const first = Number(this.index.appendF64(packed));
+    // the Buffers go to the addon as they are: it packs them with memcpy and appends in one call
+    const first = Number(this.index.appendBlobs(usable.map((r) => r.embedding)));
     usable.forEach((r, i) => this.remember(r.id, first + i));
   }
 
@@ -52,20 +82,49 @@ export class GpuEmbeddingIndex {
       this.dim = embedding.length;
       this.index = new RbkIndex(this.dim, this.device, 0);
     }
+    const slot = this.slotOfId.get(id);
     if (embedding.length !== this.dim) {
-      this.mixedLengths = true; // the reference would store it and throw on the next search
+      // the reference stores it and throws on every search until the id is deleted or re-set correctly
+      this.badIds.add(id);
+      if (slot !== undefined) {
+        this.slotOfId.delete(id);
+        this.idOfSlot[slot] = null;
+        this.index.tombstone(BigInt64Array.from([BigInt(slot)]));
+      }
       return;
     }
+    this.badIds.delete(id);
     const row = Float64Array.from(embedding);
-    const slot = this.slotOfId.get(id);
     if (slot !== undefined) this.index.overwriteF64(slot, row);
     else this.remember(id, Number(this.index.appendF64(row)));
+  }
+
+  /** addChunks: new ids are appended in one call, existing ids overwritten in one call (one host round trip each). */
+  setMany(items: Array<{ id: string; embedding: number[] }>): void {
+    const fresh = items.filter((it) => this.index && it.embedding.length === this.dim && !this.slotOfId.has(it.id));
+    const again = items.filter((it) => this.index && it.embedding.length === this.dim && this.slotOfId.has(it.id));
+    const rest = items.filter((it) => !fresh.includes(it) && !again.includes(it));
+    if (new Set(items.map((it) => it.id)).size !== items.length) return items.forEach((it) => this.set(it.id, it.embedding));
+    if (fresh.length > 0) {
+      const packed = new Float64Array(fresh.length * this.dim);
+      fresh.forEach((it, i) => packed.set(it.embedding, i * this.dim));
+      const first = Number(this.index.appendF64(packed));
+      fresh.forEach((it, i) => this.remember(it.id, first + i));
+    }
+    if (again.length > 0) {
+      const packed = new Float64Array(again.length * this.dim);
+      again.forEach((it, i) => packed.set(it.embedding, i * this.dim));
+      this.index.overwriteF64Batch(BigInt64Array.from(again.map((it) => BigInt(this.slotOfId.get(it.id)!))), packed);
+      again.forEach((it) => this.badIds.delete(it.id));
+    }
+    rest.forEach((it) => this.set(it.id, it.embedding));
   }
 
   /** Map.delete for a batch of keys. */
   deleteMany(ids: string[]): void {
     const slots: bigint[] = [];
     for (const id of ids) {
+      this.badIds.delete(id);
       const slot = this.slotOfId.get(id);
       if (slot === undefined) continue;
       this.slotOfId.delete(id);
@@ -78,18 +137,36 @@ export class GpuEmbeddingIndex {
   clear(): void {
     this.idOfSlot = [];
     this.slotOfId.clear();
-    this.mixedLengths = false;
+    this.badIds.clear();
     this.index?.clear();
   }
 
   /** The scan + threshold + stable sort + cut, for one query embedding. */
   async best(query: number[], limit: number, minScore: number): Promise<ScoredId[]> {
-    if (!this.index || this.slotOfId.size === 0) return [];
-    if (this.mixedLengths || query.length !== this.dim) throw new Error('Vectors must have the same length');
-    const { slots, scores, counts } = await this.index.search(Float64Array.from(query), 1, limit, minScore);
-    const out: ScoredId[] = [];
-    for (let i = 0; i < counts[0]; i++) out.push({ id: this.idOfSlot[Number(slots[i])]!, score: scores[i] });
-    return out;
+    return (await this.bestBatch([query], limit, minScore))[0];
+  }
+
+  /**
+   * The same for B queries in ONE device pass (what B sequential search() calls cost the reference): the entry point
+   * of the micro-batcher that coalesces concurrent searches of several investigations (SURVEY 8f-3;
+   * runbookai_b200/batcher.py is the tested mirror).  limit <= 112 per pass (RBK_MAX_K_FETCH).
+   */
+  async bestBatch(queries: number[][], limit: number, minScore: number): Promise<ScoredId[][]> {
+    if (!this.index || this.slotOfId.size === 0) return queries.map(() => []);
+    if (this.badIds.size > 0 || queries.some((q) => q.length !== this.dim)) {
+      throw new Error('Vectors must have the same length');
+    }
+    const B = queries.length;
+    const packed = new Float64Array(B * this.dim);
+    queries.forEach((q, b) => packed.set(q, b * this.dim));
+    const { slots, scores, counts } = await this.index.search(packed, B, limit, minScore);
+    return queries.map((_, b) => {
+      const out: ScoredId[] = [];
+      for (let i = 0; i < counts[b]; i++) {
+        out.push({ id: this.idOfSlot[Number(slots[b * limit + i])]!, score: scores[b * limit + i] });
+      }
+      return out;
+    });
   }
 
   private remember(id: string, slot: number): void {
