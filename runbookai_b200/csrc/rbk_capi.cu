@@ -292,9 +292,12 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
                     long long* d_slots, double* d_scores, int* d_counts, int* d_flags, float* dbg) {
   const int kprime = pick_kprime(ix, k_fetch);
   ix->stats.last_kprime = kprime;
+  // (also zeroes the scan scratch of the first sub-batch; normA is left to the finalize kernel)
+  const int Bs0 = std::min(kMaxSubBatch, B);
   CK(launch_prep_queries(d_q, src_type, B, ix->dim, ix->dpad, min_score,
                          ix->keep_f64 ? reinterpret_cast<const float*>(ix->d_counter + 1) : nullptr,
-                         query_buffers(ix, 0), ix->stream));
+                         query_buffers(ix, 0), ix->stream, /*with_norm2=*/d_counts == nullptr, ix->hist.p, Bs0,
+                         ix->sm_count + 8));
   ix->stats.kernel_launches++;
   if (ix->n_rows == 0) {
     // nothing to scan: finalize would read unwritten lists; emit empty results directly
@@ -367,9 +370,10 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
       sp.maxbin = reinterpret_cast<int*>(base + static_cast<size_t>(Bs) * kHistBins);
       sp.gthr = reinterpret_cast<unsigned int*>(sp.maxbin + Bs);
       sp.progress = sp.maxbin + 2 * Bs;
-      CK(cudaMemsetAsync(base, 0,
-                         sizeof(unsigned int) * (static_cast<size_t>(Bs) * kHistBins + 2 * Bs + ix->sm_count + 8),
-                         ix->stream));
+      if (q0 > 0)   // the first sub-batch's scratch was zeroed by the prep kernel
+        CK(cudaMemsetAsync(base, 0,
+                           sizeof(unsigned int) * (static_cast<size_t>(Bs) * kHistBins + 2 * Bs + ix->sm_count + 8),
+                           ix->stream));
     }
     sp.cand = ix->cand.p;
     sp.cand_cnt = ix->cand_cnt.p;
@@ -952,7 +956,8 @@ rbk_status rbk_index_exact_scores_f64(rbk_index* ix, const double* queries, int3
   CK(ix->o_scores.ensure(n));
   CK(cudaMemcpyAsync(ix->q_raw.p, queries, static_cast<size_t>(B) * ix->dim * 8, cudaMemcpyHostToDevice, ix->stream));
   // the prep kernel gives the f64 copy and the reference's normA; its scan-side outputs are unused here
-  CK(launch_prep_queries(ix->q_raw.p, 0, B, ix->dim, ix->dpad, -INFINITY, nullptr, query_buffers(ix, 0), ix->stream));
+  CK(launch_prep_queries(ix->q_raw.p, 0, B, ix->dim, ix->dpad, -INFINITY, nullptr, query_buffers(ix, 0), ix->stream,
+                         /*with_norm2=*/true, nullptr, 0, 0));
   CK(launch_exact_scores(ix->rows, ix->rows_f64, ix->norm2, ix->dead_bits, ix->n_rows, ix->dim, ix->dpad, ix->q_f64.p,
                          ix->q_norm2.p, B, ix->o_scores.p, ix->stream));
   ix->stats.kernel_launches += 2;

@@ -52,12 +52,30 @@ __device__ __forceinline__ double exact_cosine(double dot, double na, double nb)
 }
 
 // --------------------------------------------------------------------------- prep
-template <typename SrcT>
+// kNorm2: also compute the reference's normA (one SEQUENTIAL fp64 chain over d elements, ~30 cycles each: 12 us
+// at d = 768).  A search does not need it here: only the finalize kernel reads it, and computes it itself on an
+// otherwise idle thread beside the candidates' dot chains - so the chain left the critical path of every search.
+// The exact-scores path, which has no finalize, asks for it.
+// scratch (nullable): the per-launch scan scratch of the FIRST sub-batch - hist [Bs][kHistBins] | maxbin [Bs] |
+// gthr [Bs] | progress [n_progress] - zeroed here, one row per query block, instead of by a separate memset node.
+template <typename SrcT, bool kNorm2>
 __global__ void __launch_bounds__(128) prep_queries_kernel(const SrcT* __restrict__ src, int d, int dpad,
                                                            double min_score, double acc_eps,
-                                                           const float* __restrict__ eps_c, QueryBuffers qb) {
+                                                           const float* __restrict__ eps_c, QueryBuffers qb,
+                                                           unsigned int* __restrict__ scratch, int Bs, int n_progress) {
   const int q = blockIdx.x;
   const int tid = threadIdx.x;
+  if (scratch != nullptr && q < Bs) {
+    uint4* row = reinterpret_cast<uint4*>(scratch + static_cast<size_t>(q) * kHistBins);
+    for (int i = tid; i < kHistBins / 4; i += blockDim.x) row[i] = make_uint4(0u, 0u, 0u, 0u);
+    unsigned int* tail = scratch + static_cast<size_t>(Bs) * kHistBins;
+    if (tid == 0) {
+      tail[q] = 0u;        // maxbin
+      tail[Bs + q] = 0u;   // gthr
+    }
+    if (q == 0)
+      for (int i = tid; i < n_progress; i += blockDim.x) tail[2 * Bs + i] = 0u;
+  }
   const SrcT* s = src + static_cast<size_t>(q) * d;
   double sb = 0.0, sd = 0.0;  // ||bf16(q)||^2 and ||q - bf16(q)||^2 (any order: bounds only)
   for (int i = tid; i < dpad; i += blockDim.x) {
@@ -88,13 +106,28 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const SrcT* __restric
   // operands are staged in smem first (a dependent global load per element cost ~23 ns each).
   __shared__ double s_x[512];
   double na = 0.0;
-  for (int c0 = 0; c0 < d; c0 += 512) {
-    const int len = d - c0 < 512 ? d - c0 : 512;
+  if (kNorm2) {
+    for (int c0 = 0; c0 < d; c0 += 512) {
+      const int len = d - c0 < 512 ? d - c0 : 512;
+      __syncthreads();
+      for (int i = tid; i < len; i += blockDim.x) s_x[i] = static_cast<double>(s[c0 + i]);
+      __syncthreads();
+      if (tid == 0)
+        for (int i = 0; i < len; ++i) na = __dadd_rn(na, __dmul_rn(s_x[i], s_x[i]));
+    }
+  } else {
+    // any-order sum of squares of the f64 query: only its sign/finiteness and the ratio below (bounds) are used
+    double sq = 0.0;
+    for (int i = tid; i < d; i += blockDim.x) {
+      const double x = static_cast<double>(s[i]);
+      sq += x * x;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(kFull, sq, o);
+    __shared__ double red_q[4];
+    if ((tid & 31) == 0) red_q[tid >> 5] = sq;
     __syncthreads();
-    for (int i = tid; i < len; i += blockDim.x) s_x[i] = static_cast<double>(s[c0 + i]);
-    __syncthreads();
-    if (tid == 0)
-      for (int i = 0; i < len; ++i) na = __dadd_rn(na, __dmul_rn(s_x[i], s_x[i]));
+    na = red_q[0] + red_q[1] + red_q[2] + red_q[3];
   }
   if (tid == 0) s_na = na;
   __syncthreads();
@@ -107,12 +140,13 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const SrcT* __restric
     // angle(q, bf16(q)) <= asin(||q - bf16(q)|| / ||q||); cosine is 1-Lipschitz in the angle
     double ang = 0.0;
     if (ok && nd2 > 0.0) {
-      const double ratio = sqrt(nd2 / na) * (1.0 + 1e-9);
+      const double ratio = sqrt(nd2 / na) * (1.0 + 1e-9) * (kNorm2 ? 1.0 : 1.0 + 1e-12 * d);   // any-order sum: widen
+
       ang = ratio < 1.0 ? asin(ratio) * (1.0 + 1e-9) : 3.2;
     }
     // + corpus-side quantisation angle when the exact source is an f64 sidecar (0 for bf16-exact corpora)
     const double eps = acc_eps + ang + (eps_c != nullptr ? static_cast<double>(*eps_c) * (1.0 + 1e-6) : 0.0);
-    qb.q_norm2[q] = na;
+    if (kNorm2) qb.q_norm2[q] = na;   // (else: written by the finalize kernel, bit-exact)
     qb.q_eps[q] = eps;
     const float invf = ok ? static_cast<float>(inv) : __uint_as_float(0x7FC00000u);
     qb.q_inv_norm[q] = invf;
@@ -321,7 +355,11 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p)
   // must not sit inside it: all threads stage a K-chunk of every candidate row (and of the query)
   // into smem with the loads in flight together, then each candidate's thread walks its chunk.
   // The key staging buffer is dead by now (selection is in s_sel) and is reused for the rows.
-  const double na = p.q.q_norm2[ql];
+  // The reference's normA (embedder.ts:179: index order, multiply then add) is one more sequential fp64 chain over
+  // the query.  The last thread of the block - idle, at most kMaxKPrime threads carry candidates - walks it over the
+  // same staged query chunks the candidates' dot chains read, so it costs the search nothing.
+  __shared__ double s_na;
+  double na_chain = 0.0;
   const double* qv = p.q.q_f64 + static_cast<size_t>(ql) * p.d;
   __shared__ double s_q[kQChunk];
   unsigned char* s_rows = reinterpret_cast<unsigned char*>(s_keys);
@@ -375,6 +413,8 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p)
         for (; i < len; ++i)
           dot = __dadd_rn(dot, __dmul_rn(s_q[i], bf16_to_f64(reinterpret_cast<const uint16_t*>(mine)[i])));
       }
+      if (tid == kFinThreads - 1)
+        for (int i = 0; i < len; ++i) na_chain = __dadd_rn(na_chain, __dmul_rn(s_q[i], s_q[i]));
     }
   } else {
     // exact source = the f64 sidecar: same staging, 8-byte elements (odd stride in doubles: conflict-free)
@@ -396,8 +436,16 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p)
         const double* mine = s_rows64 + tid * row_stride;
         for (int i = 0; i < len; ++i) dot = __dadd_rn(dot, __dmul_rn(s_q[i], mine[i]));
       }
+      if (tid == kFinThreads - 1)
+        for (int i = 0; i < len; ++i) na_chain = __dadd_rn(na_chain, __dmul_rn(s_q[i], s_q[i]));
     }
   }
+  if (tid == kFinThreads - 1) {
+    s_na = na_chain;
+    p.q.q_norm2[ql] = na_chain;   // kept for the exhaustive fallback of a flagged query
+  }
+  __syncthreads();
+  const double na = s_na;
   if (tid < nsel) {
     const double sc = exact_cosine(dot, na, p.row_norm2[my_row]);
     s_score[tid] = sc;
@@ -679,13 +727,23 @@ __global__ void __launch_bounds__(128) merge_shards_kernel(int G, int B, int k, 
 }  // namespace
 
 cudaError_t launch_prep_queries(const void* src, int src_type, int B, int d, int dpad, double min_score,
-                                const float* eps_c, const QueryBuffers& qb, cudaStream_t stream) {
+                                const float* eps_c, const QueryBuffers& qb, cudaStream_t stream, bool with_norm2,
+                                unsigned int* scratch, int Bs, int n_progress) {
   if (B <= 0) return cudaSuccess;
   const double acc_eps = accumulation_eps(d);
-  if (src_type == 0)
-    prep_queries_kernel<double><<<B, 128, 0, stream>>>(static_cast<const double*>(src), d, dpad, min_score, acc_eps, eps_c, qb);
-  else
-    prep_queries_kernel<float><<<B, 128, 0, stream>>>(static_cast<const float*>(src), d, dpad, min_score, acc_eps, eps_c, qb);
+  const double* sd = static_cast<const double*>(src);
+  const float* sf = static_cast<const float*>(src);
+  if (src_type == 0) {
+    if (with_norm2)
+      prep_queries_kernel<double, true><<<B, 128, 0, stream>>>(sd, d, dpad, min_score, acc_eps, eps_c, qb, scratch, Bs, n_progress);
+    else
+      prep_queries_kernel<double, false><<<B, 128, 0, stream>>>(sd, d, dpad, min_score, acc_eps, eps_c, qb, scratch, Bs, n_progress);
+  } else {
+    if (with_norm2)
+      prep_queries_kernel<float, true><<<B, 128, 0, stream>>>(sf, d, dpad, min_score, acc_eps, eps_c, qb, scratch, Bs, n_progress);
+    else
+      prep_queries_kernel<float, false><<<B, 128, 0, stream>>>(sf, d, dpad, min_score, acc_eps, eps_c, qb, scratch, Bs, n_progress);
+  }
   return cudaGetLastError();
 }
 

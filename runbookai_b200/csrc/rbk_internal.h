@@ -120,8 +120,12 @@ struct QueryBuffers {
 };
 // src_type: 0 = f64, 1 = f32 (device pointers, row pitch d)
 // eps_c (nullable): device float, bound on the corpus-side quantisation angle (f64 sidecar indexes).
+// with_norm2: also run the sequential normA chain (only the exact-scores path, which has no finalize kernel; a
+// search leaves it to finalize).  scratch (nullable): hist | maxbin | gthr | progress of the first sub-batch (Bs
+// queries, n_progress pacing slots), zeroed by the kernel.
 cudaError_t launch_prep_queries(const void* src, int src_type, int B, int d, int dpad, double min_score,
-                                const float* eps_c, const QueryBuffers& qb, cudaStream_t stream);
+                                const float* eps_c, const QueryBuffers& qb, cudaStream_t stream, bool with_norm2,
+                                unsigned int* scratch, int Bs, int n_progress);
 
 // local row -> global slot.  Contiguous shards: slot_base + row.  A group that deals rows out block-cyclically over
 // G devices (rbk_group.cu): device g's local row r is global slot ((r / block) * G + g) * block + r % block - still
