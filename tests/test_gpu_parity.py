@@ -327,6 +327,78 @@ def test_bulk_overwrite_and_device_f64_append_match_oracle(rb, oracle_mod):
             ix.overwrite_f64_batch(np.zeros(0, dtype=np.int64), np.zeros((0, d)))     # empty batch is a no-op
 
 
+def test_any_k_exact_scores_path_matches_oracle(rb, oracle_mod):
+    """k_fetch beyond the scan's candidate lists (limit: 50 / 1000 call sites of the reference): every row's exact
+    fp64 cosine from the device, then the reference's own `>= minScore`, stable sort and slice on the host.  Same
+    ids, same fp64 scores as the oracle, for bf16 rows and for arbitrary float64 rows (f64 sidecar), with tombstones,
+    a zero row and a zero query."""
+    from runbookai_b200 import synth
+    rng = np.random.default_rng(171)
+    n, d = 5000, 200
+    for keep in (False, True):
+        corpus_bits = synth.random_corpus(n, d, 172)
+        corpus_f = rng.standard_normal((n, d)) if keep else synth.bf16_bits_to_f32(corpus_bits).astype(np.float64)
+        corpus_f[11] = 0.0
+        q = rng.standard_normal((4, d))
+        q[3] = 0.0
+        corpus_f[100:140] = q[0] * rng.uniform(0.5, 2.0, (40, 1))       # 40 exact-cosine-1 ties: stable order = slot order
+        live = np.ones(n, dtype=np.uint8)
+        dead = rng.choice(n, 300, replace=False)
+        live[dead] = 0
+        with rb.Index(d, keep_f64=keep) as ix:
+            ix.append_f64(corpus_f)
+            ix.tombstone(dead)
+            oracle_rows = corpus_f if keep else synth.f32_to_bf16_bits(corpus_f.astype(np.float32))
+            sc = ix.exact_scores(q)
+            assert sc.shape == (4, n) and np.isnan(sc[:, 11]).all() and np.isnan(sc[:, dead]).all() and np.isnan(sc[3]).all()
+            ref0 = oracle_mod.scores(oracle_rows, q[0])
+            ok = live.astype(bool) & ~np.isnan(ref0)
+            assert (sc[0, ok] == ref0[ok]).all()                      # every score bit-exact
+            for k_fetch, ms in ((113, None), (500, 0.05), (2000, None), (6000, 0.5)):
+                s_, v_, c_, _ = ix.search_any_k(q, k_fetch, ms)
+                for b in range(4):
+                    es, ev = oracle_mod.search(oracle_rows, q[b], k_fetch, ms, live=live)
+                    assert c_[b] == len(es) and (s_[b, :len(es)] == es).all() and (v_[b, :len(es)] == ev).all()
+                    assert (s_[b, len(es):] == -1).all()
+            assert (ix.search_any_k(q, 20, None)[0] == ix.search(q, 20, None)[0]).all()   # small k: the scan path
+
+
+def test_async_search_reports_unproven_queries_instead_of_fixing_them(rb, oracle_mod):
+    """rbk_index_search_device_async never synchronises, so it cannot re-answer a query whose proof failed: it
+    returns flag 1 for it (and exact answers with flag 0 for the others); the synchronous call on the same inputs
+    then gives the oracle's answer for every query."""
+    import torch
+    from runbookai_b200 import synth
+    n, d, b, k = 20_000, 128, 6, 20
+    corpus = synth.random_corpus(n, d, 181)
+    q = synth.random_queries(b, d, 182)
+    dup = np.random.default_rng(183).choice(n, 150, replace=False)
+    corpus[dup] = synth.f32_to_bf16_bits(q[2] * 0.25)                 # 150 exact ties for query 2: no margin holds them
+    dev = torch.device("cuda", 0)
+    with rb.Index(d) as ix:
+        ix.append_bf16(corpus)
+        st = torch.cuda.Stream(dev)
+        ix.set_stream(st.cuda_stream)
+        with torch.cuda.stream(st):
+            qd = torch.from_numpy(q).to(dev)
+            os_ = torch.empty((b, k), dtype=torch.int64, device=dev)
+            ov = torch.empty((b, k), dtype=torch.float64, device=dev)
+            oc = torch.empty((b,), dtype=torch.int32, device=dev)
+            of = torch.full((b,), 7, dtype=torch.int32, device=dev)
+            ix.search_device_async(qd.data_ptr(), b, k, None, os_.data_ptr(), ov.data_ptr(), oc.data_ptr(), of.data_ptr())
+        st.synchronize()
+        flags = of.cpu().numpy()
+        assert flags[2] == 1 and (np.delete(flags, 2) == 0).all()
+        es, ev, ec = oracle_mod.search_batch_verify(corpus, q.astype(np.float64), k, None)
+        for i in range(b):
+            if flags[i] == 0:
+                assert (os_[i].cpu().numpy() == es[i]).all() and (ov[i].cpu().numpy() == ev[i]).all()
+        ix.search_device(qd.data_ptr(), b, k, None, os_.data_ptr(), ov.data_ptr(), oc.data_ptr())    # synchronous: exact
+        assert (os_.cpu().numpy() == es).all() and (ov.cpu().numpy() == ev).all() and (oc.cpu().numpy() == ec).all()
+        assert os_[2].cpu().numpy().tolist() == sorted(dup.tolist())[:k]
+        ix.set_stream(None)
+
+
 def test_degenerate_inputs_and_errors(rb, native):
     from runbookai_b200 import synth
     d = 32
