@@ -48,6 +48,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     cmd = [_nvcc(), *NVCC_FLAGS, *[str(CSRC / s) for s in SOURCES], "-o", str(LIB)]
     if os.environ.get("RBK_EXPERIMENTAL") == "1":
         cmd.insert(1, "-DRBK_EXPERIMENTAL")
+    for flag in os.environ.get("RBK_EXTRA_NVCC_FLAGS", "").split():   # development probes, e.g. -DRBK_FIN_PROFILE
+        cmd.insert(1, flag)
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

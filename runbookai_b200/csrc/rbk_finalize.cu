@@ -355,6 +355,13 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeParams p)
   // must not sit inside it: all threads stage a K-chunk of every candidate row (and of the query)
   // into smem with the loads in flight together, then each candidate's thread walks its chunk.
   // The key staging buffer is dead by now (selection is in s_sel) and is reused for the rows.
+  // Cycle stamps (a clock64 probe build, round 2; 625k-row shard, B=256, d=768, 32 candidates): this phase is
+  // 26 k of the block's 44 k cycles = 34 cycles per element for conversion + DMUL + DADD in one warp.  Three
+  // rearrangements of the same operations were measured and ALL lost: widening bf16 -> binary64 with integer
+  // instructions instead of F2F (51 k cycles), forming the next group's 8 products ahead of the current group's
+  // 8 dependent adds by hand (38 k), and letting all 256 threads form the products into shared memory so that the
+  // chain thread only adds (65 k with 16-byte row loads, 110 k element-wise).  Whatever issues them, fp64-pipe
+  // instructions cost this kernel 11-27 cycles each; the loop below issues the fewest.
   // The reference's normA (embedder.ts:179: index order, multiply then add) is one more sequential fp64 chain over
   // the query.  The last thread of the block - idle, at most kMaxKPrime threads carry candidates - walks it over the
   // same staged query chunks the candidates' dot chains read, so it costs the search nothing.
