@@ -149,9 +149,11 @@ scan2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
       if (rank == 0 && lane == 0) lockstep_pace(prog, p.QB, qb, tile - t0, p.max_lead_tiles);
       __syncwarp();
       const int c_row0 = tile * kBlockN + static_cast<int>(rank) * kHalfN;
-      if (kRes && p.prefetch_tiles > 0 && tile + p.prefetch_tiles < t1 && lane == 0) {
-        // the resident layout leaves only 32 KB of smem ring per CTA: fetch this CTA's rows of a
-        // later tile into L2 now so the ring's loads are L2 hits (prefetch boxes: 128 rows x 256 cols)
+      if (p.prefetch_tiles > 0 && tile + p.prefetch_tiles < t1 && lane == 0) {
+        // HBM latency outside the smem ring: fetch this CTA's rows of a later tile into L2 now so that the ring's
+        // loads are L2 hits (prefetch boxes: 128 rows x 256 cols).  The ring holds 7 x 16 KB of corpus per SM
+        // (16.6 MB chip-wide), which at ~2 us of HBM latency caps a pure stream near 5.5 TB/s of the 7.3 TB/s that
+        // TMA reads reach on this chip (scripts/probes/tma_stream_probe.cu).
         for (int c = 0; c < p.dpad; c += 256) tma_prefetch_l2_2d(&tmap_pf, c, c_row0 + p.prefetch_tiles * kBlockN);
       }
       for (int ks = 0; ks < n_ksteps; ++ks) {
