@@ -399,6 +399,59 @@ def test_async_search_reports_unproven_queries_instead_of_fixing_them(rb, oracle
         ix.set_stream(None)
 
 
+def test_randomized_differential_against_oracle(rb, oracle_mod):
+    """A few hundred random operations - appends of random sizes, bulk overwrites, tombstones, searches with random
+    batch size / k_fetch / threshold (1-CTA and pair kernels, sub-batching, thresholds that pass nothing or
+    everything) - on one index, every search compared with the oracle on the mirrored host state."""
+    from runbookai_b200 import synth
+    rng = np.random.default_rng(2024)
+    for d, keep in ((96, False), (200, True)):
+        rows = np.zeros((0, d), dtype=np.float64)
+        live = np.zeros((0,), dtype=np.uint8)
+
+        def fresh(n):
+            x = synth.bf16_bits_to_f32(synth.random_corpus(n, d, int(rng.integers(1 << 30)))).astype(np.float64)
+            return rng.standard_normal((n, d)) if keep else x
+        with rb.Index(d, keep_f64=keep, capacity_hint=64) as ix:
+            for step in range(120):
+                op = rng.choice(["append", "append", "overwrite", "tombstone", "search", "search", "search"])
+                n = rows.shape[0]
+                if op == "append" or n < 300:
+                    m = int(rng.choice([1, 7, 255, 256, 257, 1500, 5000]))
+                    new = fresh(m)
+                    if rng.random() < 0.2:
+                        new[rng.integers(m)] = 0.0                          # a zero row: NaN, never returned
+                    assert ix.append_f64(new) == n
+                    rows = np.concatenate([rows, new])
+                    live = np.concatenate([live, np.ones(m, dtype=np.uint8)])
+                elif op == "overwrite":
+                    alive = np.flatnonzero(live)
+                    sl = rng.choice(alive, min(len(alive), int(rng.integers(1, 200))), replace=False)
+                    new = fresh(len(sl))
+                    ix.overwrite_f64_batch(sl, new)
+                    rows[sl] = new
+                elif op == "tombstone":
+                    sl = rng.choice(n, min(n, int(rng.integers(1, 400))), replace=False)
+                    ix.tombstone(sl)
+                    live[sl] = 0
+                else:
+                    b = int(rng.choice([1, 2, 5, 64, 129, 300]))
+                    k = int(rng.choice([1, 5, 16, 32, 64, 112]))
+                    ms = rng.choice([None, 0.5, 0.0, -0.05, 0.2, 0.999])
+                    ms = None if ms is None else float(ms)
+                    q = rng.standard_normal((b, d)) if rng.random() < 0.5 else synth.random_queries(b, d, int(rng.integers(1 << 30))).astype(np.float64)
+                    if rng.random() < 0.3 and rows.shape[0]:
+                        pick = rng.choice(np.flatnonzero(live)) if live.any() else 0
+                        q[0] = rows[pick] * 1.5 + 0.01 * rng.standard_normal(d)  # a near-duplicate: passes any threshold
+                    s_, v_, c_, _ = ix.search(q, k, ms)
+                    oracle_rows = rows if keep else synth.f32_to_bf16_bits(rows.astype(np.float32))
+                    for i in range(min(b, 6)):
+                        es, ev = oracle_mod.search(oracle_rows, q[i], k, ms, live=live)
+                        assert c_[i] == len(es), (d, step, i, c_[i], len(es))
+                        assert (s_[i, :len(es)] == es).all() and (v_[i, :len(es)] == ev).all(), (d, step, i)
+                assert ix.size() == rows.shape[0] and ix.count() == int(live.sum())
+
+
 def test_degenerate_inputs_and_errors(rb, native):
     from runbookai_b200 import synth
     d = 32
