@@ -80,10 +80,6 @@ rbk_status encode_rows_tmap(CUtensorMap* out, const void* base, int64_t rows, in
 
 int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
-}  // namespace
-
-namespace {
-
 cudaEvent_t get_event(rbk_index* ix, size_t i) {
   while (ix->ev.size() <= i) {
     cudaEvent_t e;
@@ -254,8 +250,11 @@ rbk_status refresh_corpus_tmap(rbk_index* ix) {
 }
 
 }  // namespace
+
+// ---- shared with rbk_group.cu (declared in rbk_index_impl.h) ----
 namespace rbk {
 namespace impl {
+
 rbk_status ensure_query_scratch(rbk_index* ix, int B, int elem) {
   CK(ix->q_raw.ensure(static_cast<size_t>(B) * ix->dim * elem));
   CK(ix->q_bf16.ensure(static_cast<size_t>(B) * ix->dpad));
@@ -272,8 +271,19 @@ rbk_status ensure_query_scratch(rbk_index* ix, int B, int elem) {
   CK(ix->hist.ensure(static_cast<size_t>(kMaxSubBatch) * kHistBins + 2 * kMaxSubBatch + ix->sm_count + 8));
   return RBK_OK;
 }
+
+rbk_status check_search_args(rbk_index* ix, int B, bool have_q, int query_dim, int k_fetch, double min_score) {
+  if (!ix) return fail(RBK_EINVAL, "null index");
+  if (B < 0 || (B > 0 && !have_q)) return fail(RBK_EINVAL, "bad queries argument");
+  if (k_fetch < 1 || k_fetch > RBK_MAX_K_FETCH) return fail(RBK_EINVAL, "k_fetch must be in [1, 112]");
+  if (query_dim != ix->dim) return fail(RBK_EDIM, "Vectors must have the same length");  // embedder.ts:170
+  if (min_score != min_score) return fail(RBK_EINVAL, "min_score is NaN");
+  return RBK_OK;
+}
+
 }  // namespace impl
 }  // namespace rbk
+
 namespace {
 
 QueryBuffers query_buffers(rbk_index* ix, int q0) {
@@ -525,25 +535,11 @@ rbk_status run_fallback(rbk_index* ix, const std::vector<int>& fails, int k_fetc
 }
 
 }  // namespace
-namespace rbk {
-namespace impl {
-rbk_status check_search_args(rbk_index* ix, int B, bool have_q, int query_dim, int k_fetch, double min_score) {
-  if (!ix) return fail(RBK_EINVAL, "null index");
-  if (B < 0 || (B > 0 && !have_q)) return fail(RBK_EINVAL, "bad queries argument");
-  if (k_fetch < 1 || k_fetch > RBK_MAX_K_FETCH) return fail(RBK_EINVAL, "k_fetch must be in [1, 112]");
-  if (query_dim != ix->dim) return fail(RBK_EDIM, "Vectors must have the same length");  // embedder.ts:170
-  if (min_score != min_score) return fail(RBK_EINVAL, "min_score is NaN");
-  return RBK_OK;
-}
-}  // namespace impl
-}  // namespace rbk
-namespace {
 
-// Enqueue-only search of device-resident queries (caller holds the lock).  No host synchronisation: the
-// exactness flags land in d_flags and are the caller's to check (rbk_index_search_device_async).
-}  // namespace
 namespace rbk {
 namespace impl {
+// Enqueue-only search of device-resident queries (caller holds the lock).  No host synchronisation: the
+// exactness flags land in d_flags and are the caller's to check (rbk_index_search_device_async, rbk_group.cu).
 rbk_status enqueue_search(rbk_index* ix, const void* d_q, int src_type, int B, int k_fetch, double min_score,
                           long long* d_slots, double* d_scores, int* d_counts, int* d_flags) {
   ix->stats.searches++;
@@ -552,6 +548,7 @@ rbk_status enqueue_search(rbk_index* ix, const void* d_q, int src_type, int B, i
 }
 }  // namespace impl
 }  // namespace rbk
+
 namespace {
 
 // Whole search, synchronous.  q_host/q_dev: exactly one is non-null.  Host outputs (h_*) may be null
