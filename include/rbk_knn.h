@@ -218,6 +218,7 @@ typedef struct {
   int32_t retry_batches;    /* batches scanned a second time with the widest candidate margin after a failed proof */
   double scan_ms_total;     /* device time of all scan kernels that have FINISHED so far (CUDA events around every launch) */
   int64_t scans_timed;      /* number of scan launches folded into scan_ms_total */
+  int64_t graph_replays;    /* small-batch host searches served by replaying the captured CUDA graph (prep + scan + finalize + copies) */
 } rbk_stats;
 /* Never blocks: folds in the scans that have finished and returns. */
 rbk_status rbk_index_stats(rbk_index* idx, rbk_stats* out);

@@ -47,7 +47,7 @@ class RbkStats(C.Structure):
         ("scan_launches", C.c_int64), ("kernel_launches", C.c_int64), ("last_scan_ms", C.c_float),
         ("last_total_ms", C.c_float), ("last_kprime", C.c_int32), ("sm_count", C.c_int32),
         ("last_ring_stages", C.c_int32), ("retry_batches", C.c_int32),
-        ("scan_ms_total", C.c_double), ("scans_timed", C.c_int64),
+        ("scan_ms_total", C.c_double), ("scans_timed", C.c_int64), ("graph_replays", C.c_int64),
     ]
 
 

@@ -402,8 +402,8 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
     sp.R_local = R;
     sp.unit_base = 0;
     sp.prog_base = 0;
-    cudaEvent_t* tev = next_scan_events(ix);
-    CK(cudaEventRecord(tev[0], ix->stream));
+    cudaEvent_t* tev = ix->capturing ? nullptr : next_scan_events(ix);
+    if (tev) CK(cudaEventRecord(tev[0], ix->stream));
     sp.prefetch_tiles = ix->prefetch_tiles;
     sp.perf_probe = ix->perf_probe;
     sp.max_lead_tiles = ix->max_lead_tiles;
@@ -462,7 +462,7 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
                       &ix->stats.last_ring_stages));
     else CK(launch_scan(tmap_q, ix->tmap_c, sp, ix->stream));
 #endif
-    CK(cudaEventRecord(tev[1], ix->stream));
+    if (tev) CK(cudaEventRecord(tev[1], ix->stream));
     ix->stats.scan_launches++;
     ix->stats.kernel_launches++;
     if (d_counts) {
@@ -551,6 +551,91 @@ rbk_status enqueue_search(rbk_index* ix, const void* d_q, int src_type, int B, i
 
 namespace {
 
+void drop_graph(rbk_index* ix) {
+  if (ix->graph_exec) cudaGraphExecDestroy(ix->graph_exec);
+  ix->graph_exec = nullptr;
+}
+
+// Small-batch fast path of search_core (caller holds the lock; scratch, o_block and h_block are allocated): replay
+// - or first capture - the graph of one whole search.  *done = true: results and flags are in h_block and every
+// query is proven exact.  *done = false: something needs the general path (a query's proof failed), which the
+// caller then runs from scratch.
+rbk_status search_graph(rbk_index* ix, const void* q_host, int elem, int B, int k_fetch, double min_score,
+                        size_t blk, size_t off_flags, bool* done) {
+  *done = false;
+  const size_t q_bytes = static_cast<size_t>(B) * ix->dim * elem;
+  CK(ix->h_q.ensure(q_bytes));
+  rbk_index::GraphKey key;
+  memset(&key, 0, sizeof key);   // compared with memcmp: padding must be defined
+  const void* ptrs[20] = {ix->rows, ix->inv_norm, ix->norm2, ix->rows_f64, ix->dead_bits, ix->d_counter, ix->q_raw.p,
+                          ix->q_bf16.p, ix->q_f64.p, ix->q_norm2.p, ix->q_eps.p, ix->q_inv_norm.p, ix->thr_init.p,
+                          ix->cand.p, ix->cand_cnt.p, ix->hist.p, ix->o_block.p, ix->h_block.p, ix->h_q.p, nullptr};
+  memcpy(key.ptr, ptrs, sizeof ptrs);
+  key.n_rows = ix->n_rows;
+  key.min_score = min_score;
+  key.B = B;
+  key.k_fetch = k_fetch;
+  key.elem = elem;
+  key.margin = ix->margin;
+  key.slot = ix->slot;
+  key.stream = ix->stream;
+  unsigned char* base = ix->o_block.p;
+  const size_t nout = static_cast<size_t>(B) * k_fetch;
+  if (!ix->graph_exec || memcmp(&key, &ix->graph_key, sizeof key) != 0) {
+    drop_graph(ix);
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(ix->stream, cudaStreamCaptureModeThreadLocal));
+    ix->capturing = true;
+    cudaError_t e = cudaMemcpyAsync(ix->q_raw.p, ix->h_q.p, q_bytes, cudaMemcpyHostToDevice, ix->stream);
+    rbk_status st = RBK_OK;
+    if (e == cudaSuccess)
+      st = run_scan(ix, ix->q_raw.p, elem == 8 ? 0 : 1, B, k_fetch, min_score, reinterpret_cast<long long*>(base),
+                    reinterpret_cast<double*>(base + nout * 8), reinterpret_cast<int*>(base + nout * 16),
+                    reinterpret_cast<int*>(base + off_flags), nullptr);
+    if (e == cudaSuccess && st == RBK_OK)
+      e = cudaMemcpyAsync(ix->h_block.p, ix->o_block.p, blk, cudaMemcpyDeviceToHost, ix->stream);
+    ix->capturing = false;
+    const cudaError_t e2 = cudaStreamEndCapture(ix->stream, &graph);   // always leave capture mode
+    if (st != RBK_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return st;
+    }
+    if (e != cudaSuccess || e2 != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      ix->use_graph = false;   // capture not possible here (e.g. the caller's stream is itself capturing): general
+      return RBK_OK;           // path from now on, no retry per search
+    }
+    e = cudaGraphInstantiate(&ix->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+      ix->graph_exec = nullptr;
+      cudaGetLastError();
+      ix->use_graph = false;
+      return RBK_OK;
+    }
+    memcpy(&ix->graph_key, &key, sizeof key);
+  }
+  memcpy(ix->h_q.p, q_host, q_bytes);
+  CK(cudaEventRecord(get_event(ix, 0), ix->stream));
+  CK(cudaGraphLaunch(ix->graph_exec, ix->stream));
+  CK(cudaEventRecord(get_event(ix, 1), ix->stream));
+  CK(cudaStreamSynchronize(ix->stream));   // the one host round trip
+  ix->stats.searches++;
+  ix->stats.queries += B;
+  ix->stats.scan_launches++;
+  ix->stats.kernel_launches += 3;           // prep, scan, finalize (inside the graph)
+  ix->stats.graph_replays++;
+  const int* h_flags = reinterpret_cast<const int*>(ix->h_block.p + off_flags);
+  for (int b = 0; b < B; ++b)
+    if (h_flags[b]) return RBK_OK;          // a proof failed: the general path re-answers the batch
+  float total = 0.f;
+  cudaEventElapsedTime(&total, get_event(ix, 0), get_event(ix, 1));
+  ix->stats.last_total_ms = total;
+  *done = true;
+  return RBK_OK;
+}
+
 // Whole search, synchronous.  q_host/q_dev: exactly one is non-null.  Host outputs (h_*) may be null
 // (device-output variant); device outputs may be null (host variant uses index scratch).
 rbk_status search_core(rbk_index* ix, const void* q_host, const void* q_dev, int elem, int B, int query_dim,
@@ -587,6 +672,18 @@ rbk_status search_core(rbk_index* ix, const void* q_host, const void* q_dev, int
   } else {
     CK(ix->h_flags.ensure(B));
     h_flags = ix->h_flags.p;
+  }
+  if (packed && q_host && B <= kBlockM && ix->n_rows > 0 && ix->use_graph) {
+    bool done = false;
+    st = search_graph(ix, q_host, elem, B, k_fetch, min_score, blk, off_flags, &done);
+    if (st != RBK_OK) return st;
+    if (done) {
+      if (ms_out) *ms_out = ix->stats.last_total_ms;
+      memcpy(h_slots, ix->h_block.p, sizeof(int64_t) * nout);
+      memcpy(h_scores, ix->h_block.p + off_scores, sizeof(double) * nout);
+      memcpy(h_counts, ix->h_block.p + off_counts, sizeof(int32_t) * B);
+      return RBK_OK;
+    }
   }
   resolve_scan_events(ix, false);
   const double scan_ms0 = ix->stats.scan_ms_total;
@@ -690,6 +787,7 @@ rbk_status rbk_index_create_ex(int32_t dim, int32_t device, int64_t capacity_hin
   ix->stats.sm_count = ix->sm_count;
 #ifdef RBK_EXPERIMENTAL   // A/B switches of development builds; the shipped library reads no environment
   if (const char* m = getenv("RBK_KNN_CLUSTER4")) ix->cluster4 = atoi(m);
+  if (const char* m = getenv("RBK_KNN_GRAPH")) ix->use_graph = atoi(m) != 0;
   if (const char* m = getenv("RBK_KNN_TAIL_PAIRS")) ix->tail_pairs = atoi(m);
   if (const char* m = getenv("RBK_KNN_TAIL_RHO")) ix->tail_rho = std::max(0.5, std::min(3.0, atof(m)));
   if (const char* m = getenv("RBK_KNN_MARGIN")) ix->margin = std::max(0, std::min(96, atoi(m)));
@@ -774,6 +872,8 @@ void rbk_index_destroy(rbk_index* ix) {
     ix->h_slots.release();
     ix->h_scores.release();
     ix->h_f32.release();
+    drop_graph(ix);
+    ix->h_q.release();
     for (cudaEvent_t e : ix->ev) cudaEventDestroy(e);
     for (auto& pr : ix->tev)
       for (cudaEvent_t e : pr)

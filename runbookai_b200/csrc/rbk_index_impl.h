@@ -131,6 +131,22 @@ struct rbk_index {
   cudaEvent_t tev[kTimingRing][2] = {};
   uint64_t tev_head = 0, tev_tail = 0;   // [tail, head) pending
   float pending_scan_ms = 0.f;           // scan time of the search being assembled (resolved pairs only)
+  // Small batches (B <= 128, host queries in, host results out) replay ONE captured CUDA graph - H2D of the
+  // queries, prep, scan, finalize, D2H of the packed block - instead of paying six API calls per search.  The
+  // graph bakes in every pointer and scalar it was captured with: `graph_key` is compared before each replay.
+  struct GraphKey {
+    const void* ptr[20];
+    int64_t n_rows;
+    double min_score;
+    int B, k_fetch, elem, margin;
+    rbk::SlotLayout slot;
+    cudaStream_t stream;
+  };
+  cudaGraphExec_t graph_exec = nullptr;
+  GraphKey graph_key;                     // meaningful only while graph_exec != nullptr
+  rbk::impl::PinBuf<unsigned char> h_q;   // pinned staging of the queries (the graph's H2D source)
+  bool capturing = false;                 // run_scan: no timing events inside a capture
+  bool use_graph = true;
   rbk_stats stats;
 };
 
