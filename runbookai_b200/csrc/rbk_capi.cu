@@ -257,7 +257,17 @@ namespace impl {
 
 rbk_status ensure_query_scratch(rbk_index* ix, int B, int elem) {
   CK(ix->q_raw.ensure(static_cast<size_t>(B) * ix->dim * elem));
-  CK(ix->q_bf16.ensure(static_cast<size_t>(B) * ix->dpad));
+  // rows padded to whole query blocks: the scan's TMA boxes are 128 query rows, and a box that hangs over the end of
+  // the tensor is zero-FILLED by the TMA unit row by row - measured: a B = 1 scan over 1M rows took 0.295 ms against
+  // 0.239 ms at B = 128 for the same bytes.  With the map covering whole blocks the pad rows are ordinary (zeroed
+  // once here) memory; they only ever feed accumulator rows of queries that do not exist.
+  {
+    const size_t want = static_cast<size_t>(round_up(B, 2 * kBlockM)) * ix->dpad;
+    if (want > ix->q_bf16.n) {
+      CK(ix->q_bf16.ensure(want));
+      CK(cudaMemsetAsync(ix->q_bf16.p, 0, ix->q_bf16.n * sizeof(uint16_t), ix->stream));
+    }
+  }
   CK(ix->q_f64.ensure(static_cast<size_t>(B) * ix->dim));
   CK(ix->q_norm2.ensure(B));
   CK(ix->q_eps.ensure(B));
@@ -363,10 +373,11 @@ rbk_status run_scan(rbk_index* ix, const void* d_q, int src_type, int B, int k_f
       R = R4 + R2;
     }
     CUtensorMap tmap_q, tmap_q64;
-    st = encode_rows_tmap(&tmap_q, ix->q_bf16.p + static_cast<size_t>(q0) * ix->dpad, Bs, ix->dpad, kBlockM);
+    const int q_rows = static_cast<int>(round_up(Bs, block_m));   // whole query blocks: no out-of-bounds box rows
+    st = encode_rows_tmap(&tmap_q, ix->q_bf16.p + static_cast<size_t>(q0) * ix->dpad, q_rows, ix->dpad, kBlockM);
     if (st != RBK_OK) return st;
     if (use4) {   // (never in the default build)
-      st = encode_rows_tmap(&tmap_q64, ix->q_bf16.p + static_cast<size_t>(q0) * ix->dpad, Bs, ix->dpad, kBlockM / 2);
+      st = encode_rows_tmap(&tmap_q64, ix->q_bf16.p + static_cast<size_t>(q0) * ix->dpad, q_rows, ix->dpad, kBlockM / 2);
       if (st != RBK_OK) return st;
     }
     ScanParams sp;
