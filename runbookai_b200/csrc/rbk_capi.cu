@@ -125,7 +125,9 @@ int64_t inv_norm_len(int64_t cap) { return round_up(cap, kBlockN) + kBlockN; }
 rbk_status ensure_capacity(rbk_index* ix, int64_t need) {
   if (need <= ix->cap) return RBK_OK;
   if (need >= (1ll << 31) - 2 * kBlockN) return fail(RBK_EINVAL, "an index shard holds at most 2^31 rows");
-  int64_t ncap = std::max<int64_t>(need, std::max<int64_t>(ix->cap * 2, 1024));
+  // whole 256-row tiles: the corpus tensor maps cover round_up(n_rows, 256) rows, so that no TMA box ever hangs over
+  // the end of the tensor (the TMA unit zero-fills out-of-bounds rows one by one - see ensure_query_scratch)
+  int64_t ncap = round_up(std::max<int64_t>(need, std::max<int64_t>(ix->cap * 2, 1024)), kBlockN);
   uint16_t* rows = nullptr;
   float* inv = nullptr;
   double* n2 = nullptr;
@@ -150,6 +152,9 @@ rbk_status ensure_capacity(rbk_index* ix, int64_t need) {
   cudaStream_t st = ix->stream;
   CK(cudaMemsetAsync(inv, 0xFF, static_cast<size_t>(inv_norm_len(ncap)) * 4, st));  // all-ones = NaN
   CK(cudaMemsetAsync(dead, 0, dead_words * 4, st));
+  // rows not (yet) appended are read by the scan as part of the last tile (their 1/||c|| is NaN: they never match)
+  CK(cudaMemsetAsync(rows + static_cast<size_t>(ix->n_rows) * ix->dpad, 0,
+                     static_cast<size_t>(ncap - ix->n_rows) * ix->dpad * 2, st));
   if (ix->n_rows > 0) {
     CK(cudaMemcpyAsync(rows, ix->rows, static_cast<size_t>(ix->n_rows) * ix->dpad * 2, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(inv, ix->inv_norm, static_cast<size_t>(ix->n_rows) * 4, cudaMemcpyDeviceToDevice, st));
@@ -229,23 +234,24 @@ int pick_kprime(const rbk_index* ix, int k_fetch) {
 }
 
 rbk_status refresh_corpus_tmap(rbk_index* ix) {
-  if (ix->tmap_c_base == ix->rows && ix->tmap_c_rows == ix->n_rows) return RBK_OK;
-  rbk_status st = encode_rows_tmap(&ix->tmap_c, ix->rows, ix->n_rows, ix->dpad, kBlockN);
+  const int64_t map_rows = round_up(ix->n_rows, kBlockN);   // whole tiles (<= cap): no out-of-bounds box rows
+  if (ix->tmap_c_base == ix->rows && ix->tmap_c_rows == map_rows) return RBK_OK;
+  rbk_status st = encode_rows_tmap(&ix->tmap_c, ix->rows, map_rows, ix->dpad, kBlockN);
   if (st != RBK_OK) return st;
-  st = encode_rows_tmap(&ix->tmap_c_half, ix->rows, ix->n_rows, ix->dpad, kBlockN / 2);
+  st = encode_rows_tmap(&ix->tmap_c_half, ix->rows, map_rows, ix->dpad, kBlockN / 2);
   if (st != RBK_OK) return st;
-  st = encode_rows_tmap(&ix->tmap_c_quarter, ix->rows, ix->n_rows, ix->dpad, kBlockN / 4);
+  st = encode_rows_tmap(&ix->tmap_c_quarter, ix->rows, map_rows, ix->dpad, kBlockN / 4);
   if (st != RBK_OK) return st;
 #ifdef RBK_EXPERIMENTAL
-  st = encode_rows_tmap(&ix->tmap_c_half32, ix->rows, ix->n_rows, ix->dpad, kBlockN / 2, 32);
+  st = encode_rows_tmap(&ix->tmap_c_half32, ix->rows, map_rows, ix->dpad, kBlockN / 2, 32);
   if (st != RBK_OK) return st;
-  st = encode_rows_tmap(&ix->tmap_c_pf, ix->rows, ix->n_rows, ix->dpad, kBlockN / 2, 256);
+  st = encode_rows_tmap(&ix->tmap_c_pf, ix->rows, map_rows, ix->dpad, kBlockN / 2, 256);
   if (st != RBK_OK) return st;
-  st = encode_rows_tmap(&ix->tmap_c_r32, ix->rows, ix->n_rows, ix->dpad, scan3_box_rows());
+  st = encode_rows_tmap(&ix->tmap_c_r32, ix->rows, map_rows, ix->dpad, scan3_box_rows());
   if (st != RBK_OK) return st;
 #endif
   ix->tmap_c_base = ix->rows;
-  ix->tmap_c_rows = ix->n_rows;
+  ix->tmap_c_rows = map_rows;
   return RBK_OK;
 }
 
@@ -790,7 +796,8 @@ rbk_status rbk_index_create_ex(int32_t dim, int32_t device, int64_t capacity_hin
   rbk_index* ix = new (std::nothrow) rbk_index();
   if (!ix) return fail(RBK_ENOMEM, "out of host memory");
   ix->dim = dim;
-  ix->dpad = static_cast<int>(round_up(dim, 8));
+  // row pitch = whole 64-element k-blocks (128 bytes): no TMA box hangs over the end of a row either
+  ix->dpad = static_cast<int>(round_up(dim, kBlockK));
   ix->device = device;
   ix->keep_f64 = (flags & RBK_INDEX_KEEP_F64) != 0;
   ix->sm_count = prop.multiProcessorCount;

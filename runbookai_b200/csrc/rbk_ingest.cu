@@ -50,7 +50,11 @@ __global__ void __launch_bounds__(256) convert_rows_kernel(const SrcT* __restric
       }
     }
     uint16_t o[8];
-    if (aligned) {
+    if (c0 >= d) {
+      // pad columns (the row pitch is a whole number of 64-element k-blocks): zeros, and nothing to read
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0;
+    } else if (aligned) {
       if constexpr (sizeof(SrcT) == 8) {
         const double2* s2 = reinterpret_cast<const double2*>(s);
 #pragma unroll
