@@ -128,6 +128,26 @@ def ptr(a: np.ndarray | None):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def _search_any_k(ix, queries, k_fetch: int, min_score):
+    """Shared by Index and Group: the scan path up to RBK_MAX_K_FETCH hits per query, beyond it the exact scores of
+    every row from the device and the reference's threshold / stable sort / slice on the host."""
+    if k_fetch <= RBK_MAX_K_FETCH:
+        return ix.search(queries, k_fetch, min_score)
+    sc = ix.exact_scores(queries)
+    B = sc.shape[0]
+    slots = np.full((B, k_fetch), -1, dtype=np.int64)
+    scores = np.full((B, k_fetch), np.nan, dtype=np.float64)
+    counts = np.zeros(B, dtype=np.int32)
+    for b in range(B):
+        with np.errstate(invalid="ignore"):
+            keep = np.flatnonzero(sc[b] >= min_score) if min_score is not None else np.flatnonzero(~np.isnan(sc[b]))
+        order = keep[np.argsort(-sc[b, keep], kind="stable")][:k_fetch]
+        counts[b] = len(order)
+        slots[b, :len(order)] = order
+        scores[b, :len(order)] = sc[b, order]
+    return slots, scores, counts, 0.0
+
+
 class Index:
     """Thin object wrapper over rbk_index* (one GPU shard)."""
 
@@ -250,21 +270,7 @@ class Index:
     def search_any_k(self, queries, k_fetch: int, min_score: float | None = 0.5):
         """search() for any k_fetch: above RBK_MAX_K_FETCH the answer is cut on the host from exact_scores() with the
         reference's own steps - `>= minScore`, stable descending sort over slot order, slice (vector-store.ts:212-221)."""
-        if k_fetch <= RBK_MAX_K_FETCH:
-            return self.search(queries, k_fetch, min_score)
-        sc = self.exact_scores(queries)
-        B = sc.shape[0]
-        slots = np.full((B, k_fetch), -1, dtype=np.int64)
-        scores = np.full((B, k_fetch), np.nan, dtype=np.float64)
-        counts = np.zeros(B, dtype=np.int32)
-        for b in range(B):
-            with np.errstate(invalid="ignore"):
-                keep = np.flatnonzero(sc[b] >= min_score) if min_score is not None else np.flatnonzero(~np.isnan(sc[b]))
-            order = keep[np.argsort(-sc[b, keep], kind="stable")][:k_fetch]
-            counts[b] = len(order)
-            slots[b, :len(order)] = order
-            scores[b, :len(order)] = sc[b, order]
-        return slots, scores, counts, 0.0
+        return _search_any_k(self, queries, k_fetch, min_score)
 
     def search_device(self, q_ptr: int, B: int, k_fetch: int, min_score: float | None, slots_ptr: int,
                       scores_ptr: int, counts_ptr: int) -> None:
@@ -376,6 +382,27 @@ class Group:
         ms_arg = -np.inf if min_score is None else float(min_score)
         check(fn(self._h, ptr(q), B, q.shape[1], k_fetch, ms_arg, ptr(slots), ptr(scores), ptr(counts), C.byref(ms)))
         return slots, scores, counts, ms.value
+
+    def exact_scores(self, queries) -> np.ndarray:
+        """float64 [B, size()]: every device's exact scores, put back in global slot order (4096-row blocks dealt
+        out round-robin)."""
+        q = np.ascontiguousarray(np.atleast_2d(np.asarray(queries, dtype=np.float64)))
+        n, G, blk = self.size(), len(self.devices), 4096
+        out = np.full((q.shape[0], n), np.nan, dtype=np.float64)
+        glob = np.arange(n, dtype=np.int64)
+        owner = (glob // blk) % G
+        for g in range(G):
+            member = C.c_void_p(lib.rbk_group_member(self._h, g))
+            m = lib.rbk_index_size(member)
+            if m == 0:
+                continue
+            part = np.empty((q.shape[0], m), dtype=np.float64)
+            check(lib.rbk_index_exact_scores_f64(member, ptr(q), q.shape[0], q.shape[1], ptr(part)))
+            out[:, glob[owner == g]] = part          # local row order == global slot order within a device
+        return out
+
+    def search_any_k(self, queries, k_fetch: int, min_score: float | None = 0.5):
+        return _search_any_k(self, queries, k_fetch, min_score)
 
     def stats(self) -> dict:
         out = {"devices": len(self.devices), "redone_batches": lib.rbk_group_redone_batches(self._h)}

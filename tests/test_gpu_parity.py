@@ -200,6 +200,10 @@ def test_group_one_handle_many_gpus_matches_oracle(rb, oracle_mod):
         assert g.stats()["redone_batches"] >= 1
         with pytest.raises(rb.DimensionError, match="Vectors must have the same length"):
             g.search(np.ones((1, d + 1)), 4, 0.5)
+        s_, v_, c_, _ = g.search_any_k(q[:3].astype(np.float64), 400, None)      # beyond the scan's lists: exact scores
+        for b in range(3):
+            es, ev = oracle_mod.search(corpus, q[b].astype(np.float64), 400, None, live=live)
+            assert c_[b] == len(es) and (s_[b, :len(es)] == es).all() and (v_[b, :len(es)] == ev).all()
         g.clear()
         assert g.size() == 0 and g.search(q, 5, None)[2].sum() == 0
         assert g.append_bf16(corpus[:5000]) == 0
