@@ -356,6 +356,11 @@ def run_workload(ctx, args, name, wl, main: bool, steps: int):
         ctx.sampler.window(t_region0, t_region1)
         clocks = ctx.sampler.stop()
 
+    # ---------------- same box, same power state: the plain library GEMM of this shape ----------------
+    same_box = None
+    if main and world == 1 and not l2_flush and not args.no_cublas:
+        same_box = cublas_same_box(ix, searcher, q_dev, k_fetch, args.min_score, hi - lo, d, B, steps)
+
     # ---------------- e2e: host buffers through the public call ----------------
     def e2e_step():
         if world == 1:
@@ -432,12 +437,80 @@ def run_workload(ctx, args, name, wl, main: bool, steps: int):
         }
         if clocks is not None:
             res["clocks"] = clocks
+        if same_box is not None:
+            roof["same_box_cublas"] = same_box
         if main and not args.no_cpu_baseline and world == 1:
             res["cpu_baseline"] = cpu_baseline(ctx, ix, n, n_local, d, B, k_fetch, q_np)
     ix.close()
     del searcher, flush_buf
     torch.cuda.empty_cache()
     return res
+
+
+def cublas_same_box(ix, searcher, q_dev, k_fetch, min_score, n_local, d, B, steps):
+    """What the library GEMM of the same shape does on THIS box in THIS power state: torch.matmul (cuBLAS, bf16 in,
+    fp32 accumulate, bf16 out) of the B x d query block against n_local x d rows, in 1M-row pieces, interleaved with
+    the scan in two rounds of `steps` passes each.  It only computes the score matrix (and writes it: 2*B bytes per
+    row, which the scan never does) - no threshold, no top-k, no exact re-rank - so it is the roof a power-capped
+    scan of this shape can be held against when boxes differ by 18 % on the identical kernel.  Measurement only:
+    nothing the product runs goes through it."""
+    import torch
+    device, stream = q_dev.device, searcher.stream
+    piece = -(-n_local // -(-n_local // (1 << 20)))      # ~1M-row pieces of equal size
+    with torch.cuda.stream(stream):
+        c = torch.randn(piece, d, device=device, dtype=torch.float32).to(torch.bfloat16)
+        qb = q_dev.to(torch.bfloat16)
+        out = torch.empty(B, piece, device=device, dtype=torch.bfloat16)
+        full, rest = divmod(n_local, piece)
+
+        def gemm_pass():
+            for _ in range(full):
+                torch.matmul(qb, c.t(), out=out)
+            if rest:
+                torch.matmul(qb, c[:rest].t(), out=out[:, :rest])
+        gemm_pass()
+        # the same flops as ONE GEMM with a `full` times deeper K: 1/full of the output bytes, cuBLAS at its best on
+        # this box (what MEASURED_PEAKS.json's sustained figure measures elsewhere)
+        deep = full >= 2 and rest == 0 and 2.0 * piece * d * full < 40e9
+        if deep:
+            c2 = torch.randn(piece, d * full, device=device, dtype=torch.bfloat16)
+            q2 = torch.randn(B, d * full, device=device, dtype=torch.bfloat16)
+            torch.matmul(q2, c2.t(), out=out)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+        st0 = ix.stats()
+        e[0].record(stream)
+        for r in range(2):
+            for _ in range(steps):
+                flags = searcher.search_device_async(q_dev, k_fetch, min_score)[3]
+            e[2 * r + 1].record(stream)
+            for _ in range(steps):
+                gemm_pass()
+            e[2 * r + 2].record(stream)
+        if deep:
+            for _ in range(steps):
+                torch.matmul(q2, c2.t(), out=out)
+            e[5].record(stream)
+            for _ in range(steps):
+                flags = searcher.search_device_async(q_dev, k_fetch, min_score)[3]
+            e[6].record(stream)
+    stream.synchronize()
+    searcher._dirty_seen = int(flags[-1].item())
+    st1 = ix.stats()
+    step_ms = [e[0].elapsed_time(e[1]) / steps, e[2].elapsed_time(e[3]) / steps]
+    gemm_ms = [e[1].elapsed_time(e[2]) / steps, e[3].elapsed_time(e[4]) / steps]
+    scan_ms = (st1["scan_ms_total"] - st0["scan_ms_total"]) / max(1, st1["scans_timed"] - st0["scans_timed"])
+    flops = 2.0 * B * n_local * d
+    deep_ms = e[4].elapsed_time(e[5]) / steps if deep else None
+    if deep:
+        step_ms.append(e[5].elapsed_time(e[6]) / steps)
+        del c2, q2
+    del c, out, qb
+    return {"gemm_ms": gemm_ms, "gemm_deep_k_ms": deep_ms,
+            "gemm_deep_k_tflops": flops / (deep_ms * 1e-3) / 1e12 if deep else None, "search_step_ms": step_ms, "scan_kernel_ms": scan_ms,
+            "gemm_tflops": flops / (min(gemm_ms) * 1e-3) / 1e12, "scan_tflops": flops / (scan_ms * 1e-3) / 1e12,
+            "scan_over_gemm": min(gemm_ms) / scan_ms,
+            "what": f"torch.matmul bf16 [{B}x{d}] x [{d}x{piece}] -> bf16, {full + (1 if rest else 0)} pieces per pass; "
+                    f"2 rounds of {steps} search steps then {steps} GEMM passes, back to back on one stream"}
 
 
 def cpu_baseline(ctx, ix, n, n_local, d, B, k_fetch, q_np):
@@ -475,6 +548,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override N_docs (debug only; marks the run reduced)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check (debug only)")
+    ap.add_argument("--no-cublas", action="store_true", help="skip the same-box library-GEMM comparison")
     ap.add_argument("--no-extras", action="store_true",
                     help="only the main workload (default: also cfg5 at every N and cfg4 at N=8, in `extra_workloads`)")
     ap.add_argument("--min-score", type=float, default=None,
