@@ -2,6 +2,7 @@
 """bench.py — kNN queries/sec of the knowledge-base search path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3] [--impl ours|reference] [--no-extras]
+    python bench.py --gpus N --single-process      (no torchrun: ONE process, one rbk_group handle over N GPUs)
 
 A "step" is one pass of the hot path (batched cosine scan + exact top-k) over one batch of
 B synthetic queries against the resident synthetic corpus.  Workloads are BASELINE.json's
@@ -447,6 +448,99 @@ def run_workload(ctx, args, name, wl, main: bool, steps: int):
     return res
 
 
+def run_group(args, name, wl, pk, synth, reduced):
+    """`--single-process`: the deployment one Node process would use - ONE host process, one `rbk_group` handle over
+    `--gpus` devices (include/rbk_knn.h; per-GPU scans, one ncclAllGather, merge on the first device and one
+    synchronisation inside every call).  The group's search takes host queries and returns host results, so the
+    number measured here is the end-to-end one; the corpus is the same global corpus as the torchrun mode
+    (generated on GPU 0 chunk by chunk, staged through host memory, dealt out by the library)."""
+    import torch
+    import oracle
+    from runbookai_b200 import Group
+    n, d, B, k, desc = wl
+    k_fetch = 2 * k
+    G = args.gpus
+    dev0 = torch.device("cuda", 0)
+    grp = Group(d, list(range(G)), capacity_hint=n)
+    host = np.empty((n, d), dtype=np.uint16)
+    gen = torch.Generator(device=dev0)
+    t0 = time.perf_counter()
+    for c in range(-(-n // GEN_CHUNK)):
+        gen.manual_seed(SEED * 1_000_003 + c)
+        t = torch.randn(GEN_CHUNK, d, device=dev0, generator=gen, dtype=torch.float32).to(torch.bfloat16)
+        m = min(GEN_CHUNK, n - c * GEN_CHUNK)
+        host[c * GEN_CHUNK:c * GEN_CHUNK + m] = t[:m].view(torch.int16).cpu().numpy().view(np.uint16)
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for r0 in range(0, n, 1 << 20):
+        grp.append_bf16(host[r0:r0 + (1 << 20)])
+    t_load = time.perf_counter() - t0
+    q_np = synth.random_queries(B, d, SEED + 1)
+    sampler = ClockSampler(0)
+    sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        got = grp.search(q_np, k_fetch, args.min_score)
+    st0 = grp.stats()
+    t_r0 = time.monotonic()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        got = grp.search(q_np, k_fetch, args.min_score)
+        dev_ms += got[3]
+    dt = time.perf_counter() - t0
+    t_r1 = time.monotonic()
+    st1 = grp.stats()
+    time.sleep(0.05)
+    sampler.window(t_r0, t_r1)
+    clocks = sampler.stop()
+    # parity: the first 64 queries against the oracle over all rows (host copy of the corpus)
+    oracle.build()
+    nq = min(PARITY_QUERIES, B)
+    qd = q_np[:nq].astype(np.float64)
+    t0 = time.perf_counter()
+    parts = [oracle.search_batch_verify(host[r0:r0 + (1 << 19)], qd, k_fetch, args.min_score, slot_base=r0)
+             for r0 in range(0, n, 1 << 19)]
+    es, ev, ec = oracle.merge_lists(parts, k_fetch)
+    s, v, c = got[0], got[1], got[2]
+    id_mis = score_mis = count_mis = 0
+    for b in range(nq):
+        if c[b] != ec[b]:
+            count_mis += 1
+            continue
+        m = ec[b]
+        id_mis += int((s[b, :m] != es[b, :m]).sum())
+        score_mis += int((v[b, :m] != ev[b, :m]).sum())
+    per0, per1 = st0["per_device"], st1["per_device"]
+    scan_ms = [(b_["scan_ms_total"] - a_["scan_ms_total"]) / max(1, b_["scans_timed"] - a_["scans_timed"])
+               for a_, b_ in zip(per0, per1)]
+    flops = 2.0 * B * n * d / G
+    e2e = B * args.steps / dt
+    out = {"metric": "knn_queries_per_sec", "value": e2e, "unit": "queries/s", "n_gpus": G, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": desc + (" [REDUCED rows: debug run]" if reduced else ""), "n_docs": n, "dim": d,
+                      "batch": B, "k": k, "k_fetch": k_fetch, "min_score": args.min_score,
+                      "parallelism": f"ONE process, rbk_group over {G} GPUs: rows dealt out in 4096-row blocks, per-GPU "
+                                     "scans + one ncclAllGather + merge inside rbk_group_search_f32",
+                      "value_is": "end to end (host queries in, host results out): the group call has no "
+                                  "device-resident variant", "gen_s": round(t_gen, 1), "load_s": round(t_load, 1),
+                      "redone_batches": st1["redone_batches"], "fallback_queries": st1["fallback_queries"]},
+           "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": B * d * 4 * G,
+                   "d2h_bytes_per_step": B * k_fetch * 16 + B * 4, "ms_per_step": dt / args.steps * 1e3,
+                   "device_ms_per_step": dev_ms / args.steps},
+           "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"] + args.steps * (1 + G)),
+           "roofline": {"bound": "tensor" if B > pk["tf"] * 1e12 / (pk["hbm"] * 1e9) else "hbm",
+                        "kernel_ms_per_device": scan_ms, "unit": "TFLOP/s", "peak": pk["tf"], "peak_kind": "burst",
+                        "achieved": flops / (max(scan_ms) * 1e-3) / 1e12,
+                        "frac": flops / (max(scan_ms) * 1e-3) / 1e12 / pk["tf"], "traffic": None},
+           "parity": {"queries": nq, "rows_checked": n, "k_fetch": k_fetch, "id_mismatch": id_mis,
+                      "score_mismatch": score_mis, "count_mismatch": count_mis,
+                      "seconds": round(time.perf_counter() - t0, 1)},
+           "clocks": clocks}
+    grp.close()
+    print(json.dumps(out), flush=True)
+
+
 def cublas_same_box(ix, searcher, q_dev, k_fetch, min_score, n_local, d, B, steps):
     """What the library GEMM of the same shape does on THIS box in THIS power state: torch.matmul (cuBLAS, bf16 in,
     fp32 accumulate, bf16 out) of the B x d query block against n_local x d rows, in 1M-row pieces, interleaved with
@@ -549,6 +643,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check (debug only)")
     ap.add_argument("--no-cublas", action="store_true", help="skip the same-box library-GEMM comparison")
+    ap.add_argument("--single-process", action="store_true",
+                    help="ONE process, one rbk_group handle over --gpus devices (no torchrun): the deployment a single "
+                         "Node process would use")
     ap.add_argument("--no-extras", action="store_true",
                     help="only the main workload (default: also cfg5 at every N and cfg4 at N=8, in `extra_workloads`)")
     ap.add_argument("--min-score", type=float, default=None,
@@ -575,6 +672,10 @@ def main():
     ctx.pk = peaks()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: this engine has no CPU path")
+    if args.single_process:
+        assert ctx.world == 1, "--single-process is not launched with torchrun"
+        run_group(args, args.workload, wl, ctx.pk, ctx.synth, reduced)
+        return
     torch.cuda.set_device(ctx.local)
     ctx.device = torch.device("cuda", ctx.local)
     if ctx.world > 1:
