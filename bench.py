@@ -360,7 +360,11 @@ def run_workload(ctx, args, name, wl, main: bool, steps: int):
     # ---------------- same box, same power state: the plain library GEMM of this shape ----------------
     same_box = None
     if main and world == 1 and not l2_flush and not args.no_cublas:
-        same_box = cublas_same_box(ix, searcher, q_dev, k_fetch, args.min_score, hi - lo, d, B, steps)
+        try:
+            same_box = cublas_same_box(ix, searcher, q_dev, k_fetch, args.min_score, hi - lo, d, B, steps)
+        except Exception as e:   # a comparison must never cost the headline line
+            same_box = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
 
     # ---------------- e2e: host buffers through the public call ----------------
     def e2e_step():
