@@ -81,7 +81,9 @@ rbk_status rbk_index_set_slot_base(rbk_index* idx, int64_t slot_base);
 /* rows: n_rows x dim, row-major.  f64 is the SQLite BLOB layout (little-endian float64,
  * vector-store.ts:71-88).  Values are stored as bf16 (round-to-nearest-even); the index
  * is exact for inputs representable in bf16.  first_slot_out (nullable)
- * receives the LOCAL slot of the first appended row. */
+ * receives the LOCAL slot of the first appended row.  `rows` (host memory, pageable or
+ * page-locked, or device memory for the *_device variants) has been consumed when the
+ * call returns; the conversion itself may still be running on the index's stream. */
 rbk_status rbk_index_append_f64(rbk_index* idx, const double* rows, int64_t n_rows, int64_t* first_slot_out);
 rbk_status rbk_index_append_f32(rbk_index* idx, const float* rows, int64_t n_rows, int64_t* first_slot_out);
 rbk_status rbk_index_append_bf16(rbk_index* idx, const uint16_t* rows, int64_t n_rows, int64_t* first_slot_out);
@@ -96,8 +98,8 @@ rbk_status rbk_index_overwrite_f64(rbk_index* idx, int64_t local_slot, const dou
 /* The same for n rows at once - a re-embedded document (addChunks over existing ids, vector-store.ts:135-183):
  * rows[i] (n x dim, f64) replaces local_slots[i].  One call, one host round trip for the whole batch.  A slot that
  * is tombstoned stays dead and makes the call return RBK_EINVAL after the LIVE slots of the batch have been
- * written (the host mirror never overwrites a deleted id, so this is a caller bug, not a data path).  local_slots
- * must be distinct (the host mirror keeps the last value per id). */
+ * written (the host mirror never overwrites a deleted id, so this is a caller bug, not a data path).  A slot named
+ * more than once takes its LAST row, as Map.set twice would. */
 rbk_status rbk_index_overwrite_f64_batch(rbk_index* idx, const int64_t* local_slots, int64_t n, const double* rows);
 /* `this.embeddings.delete(id)`: the rows stop matching; slots are not reused. */
 rbk_status rbk_index_tombstone(rbk_index* idx, const int64_t* local_slots, int64_t n);

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "rbk_index_impl.h"
@@ -79,6 +80,17 @@ rbk_status encode_rows_tmap(CUtensorMap* out, const void* base, int64_t rows, in
 }
 
 int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// Page-locked (or managed) host memory: cudaMemcpyAsync from it returns before the bytes have been read, unlike a copy
+// from pageable memory, which the driver stages before returning.
+bool host_source_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
 
 cudaEvent_t get_event(rbk_index* ix, size_t i) {
   while (ix->ev.size() <= i) {
@@ -220,8 +232,9 @@ rbk_status append_rows(rbk_index* ix, const void* src, bool is_device, int elem,
   ix->stats.kernel_launches += ix->keep_f64 ? 2 : 1;
   // Host sources: pageable H2D copies have consumed the caller's buffer when cudaMemcpyAsync returns and everything
   // after is stream-ordered, so an append costs no host round trip.  Device sources are read by the copy/convert
-  // kernel itself: the caller may free them as soon as we return, so wait for that.
-  if (is_device) CK(cudaStreamSynchronize(ix->stream));
+  // kernel itself, and page-locked host sources by a copy that really is asynchronous: the caller may free or reuse
+  // either as soon as we return, so wait for those.
+  if (is_device || host_source_is_pinned(src)) CK(cudaStreamSynchronize(ix->stream));
   ix->n_rows += n;
   ix->n_live += n;
   return RBK_OK;
@@ -948,6 +961,28 @@ rbk_status rbk_index_overwrite_f64_batch(rbk_index* ix, const int64_t* slots, in
   DeviceGuard dg(ix->device);
   for (int64_t i = 0; i < n; ++i)
     if (slots[i] < 0 || slots[i] >= ix->n_rows) return fail(RBK_EINVAL, "slot out of range");
+  // The same slot twice in one batch is Map.set twice: the LAST value wins (and two thread blocks scattering into one
+  // row would race).  Keep each slot's last occurrence; the common case (no repeats) copies nothing.
+  std::vector<int64_t> u_slots;
+  std::vector<double> u_rows;
+  if (n > 1) {
+    std::unordered_map<int64_t, int64_t> last;
+    last.reserve(static_cast<size_t>(n) * 2);
+    for (int64_t i = 0; i < n; ++i) last[slots[i]] = i;
+    if (static_cast<int64_t>(last.size()) != n) {
+      u_slots.reserve(last.size());
+      u_rows.resize(last.size() * static_cast<size_t>(ix->dim));
+      for (int64_t i = 0; i < n; ++i) {
+        if (last[slots[i]] != i) continue;
+        memcpy(u_rows.data() + u_slots.size() * static_cast<size_t>(ix->dim), rows + static_cast<size_t>(i) * ix->dim,
+               static_cast<size_t>(ix->dim) * 8);
+        u_slots.push_back(slots[i]);
+      }
+      slots = u_slots.data();
+      rows = u_rows.data();
+      n = static_cast<int64_t>(u_slots.size());
+    }
+  }
   // one H2D of the slots, one of the rows (chunked through the staging buffer), two kernels per chunk that scatter
   // into the named slots and skip tombstoned ones on the device, ONE host round trip for the whole batch
   const size_t row_bytes = static_cast<size_t>(ix->dim) * 8;

@@ -326,6 +326,8 @@ class VectorStore:
         slot = self._slot_of.get(vid)
         if e.shape[0] != ix.dim:
             # the reference stores it and throws on every search until the id is deleted or re-set correctly
+            # (deviation, tie order only: once re-set correctly the id is appended as a new key here, while the
+            # reference's Map kept the key's original position all along)
             self._st.bad_ids.add(vid)
             if slot is not None:          # the old, well-formed vector is no longer in the Map either
                 self._slot_of.pop(vid, None)
@@ -378,28 +380,39 @@ class VectorStore:
                                                float_array_to_buffer(e), ch["content"],
                                                ch.get("sectionTitle") or c["documentTitle"], c["type"],
                                                json.dumps(list(c["services"]), separators=(",", ":"))))
-        # bulk path: brand-new ids are appended in one call, re-sets are overwritten in place
-        fresh: list[tuple[str, np.ndarray]] = []
-        for c, e in zip(chunks, embeddings):
-            vid = f"vec_{c['chunk']['id']}"
-            if vid in self._slot_of or any(v == vid for v, _ in fresh) or (
-                    self._index is not None and len(e) != self._index.dim):
-                for v, fe in fresh:
-                    self._set(v, fe)
-                fresh = []
-                self._set(vid, e)
-            else:
-                fresh.append((vid, np.asarray(e, dtype=np.float64)))
+        self._set_many([(f"vec_{c['chunk']['id']}", e) for c, e in zip(chunks, embeddings)])
+
+    def _set_many(self, items) -> None:
+        """`this.embeddings.set(id, e)` for every item in order (vector-store.ts:178), as TWO engine calls: the
+        re-sets of ids already in the Map in one `overwrite_f64_batch` (a re-embedded document: one host round trip,
+        not one per chunk), the new ids in one `append_f64`.  Same final Map as the sequential sets: an existing key
+        keeps its position, new keys are appended in order of first appearance, the last value of a key wins."""
+        items = [(v, np.asarray(e, dtype=np.float64)) for v, e in items]
+        if not items:
+            return
+        dim = self._index.dim if self._index is not None else items[0][1].shape[0]
+        if any(e.ndim != 1 or e.shape[0] != dim for _, e in items):
+            for v, e in items:            # a wrong-length vector in the batch: the careful path, one by one
+                self._set(v, e)
+            return
+        ix = self._ensure_index(dim)
+        last: dict[str, np.ndarray] = {}
+        fresh: list[str] = []
+        for v, e in items:
+            if v not in self._slot_of and v not in last:
+                fresh.append(v)
+            last[v] = e
+        again = [v for v in last if v in self._slot_of]
+        if again:
+            ix.overwrite_f64_batch([self._slot_of[v] for v in again], np.stack([last[v] for v in again]))
         if fresh:
-            dim = fresh[0][1].shape[0]
-            if all(fe.shape[0] == dim for _, fe in fresh) and (self._index is None or self._index.dim == dim):
-                first = self._ensure_index(dim).append_f64(np.stack([fe for _, fe in fresh]))
-                for i, (v, _) in enumerate(fresh):
-                    self._slot_of[v] = first + i
-                    self._ids.append(v)
-            else:
-                for v, fe in fresh:
-                    self._set(v, fe)
+            first = ix.append_f64(np.stack([last[v] for v in fresh]))
+            for i, v in enumerate(fresh):
+                self._slot_of[v] = first + i
+                while len(self._ids) < first + i:
+                    self._ids.append(None)
+                self._ids.append(v)
+        self._st.bad_ids.difference_update(last)
 
     def delete_document(self, document_id: str) -> None:
         """vector-store.ts:285-297."""

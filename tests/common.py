@@ -49,7 +49,15 @@ class OracleIndex:
         return first
 
     def overwrite_f64(self, slot, row):
+        self.calls = getattr(self, "calls", 0) + 1
         self.rows[slot] = self._bits(np.asarray(row)[None, :])[0]
+
+    def overwrite_f64_batch(self, slots, rows):
+        """rbk_index_overwrite_f64_batch: one call; a slot named twice takes its last row."""
+        self.calls = getattr(self, "calls", 0) + 1
+        rows = np.asarray(rows, dtype=np.float64).reshape(-1, self.dim)
+        for s, r in zip(slots, rows):
+            self.rows[int(s)] = self._bits(r[None, :])[0]
 
     def tombstone(self, slots):
         self.live[np.asarray(slots, dtype=np.int64)] = 0

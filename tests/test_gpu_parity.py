@@ -329,6 +329,17 @@ def test_bulk_overwrite_and_device_f64_append_match_oracle(rb, oracle_mod):
             assert ix.search(q[:1], 3, None)[0][0, 0] in (slots[0], slots[9])
             assert ix.count() == n - 200
             ix.overwrite_f64_batch(np.zeros(0, dtype=np.int64), np.zeros((0, d)))     # empty batch is a no-op
+            # a slot named twice takes its LAST row (Map.set twice); a page-locked source may be reused on return
+            rep = np.array([slots[20], slots[21], slots[20], slots[22], slots[20]])
+            vals = np.stack([q[1] * 2.0, q[2], q[3], q[2], q[4] * 5.0])
+            ix.overwrite_f64_batch(rep, vals)
+            top = ix.search(q[:5], 4, None)[0]
+            assert slots[20] in top[4] and slots[20] not in top[1] and slots[20] not in top[3]
+            want = synth.random_corpus(64, d, 999)
+            pinned = torch.from_numpy(synth.bf16_bits_to_f32(want).astype(np.float64)).pin_memory()
+            first = ix.append_f64(pinned.numpy())
+            pinned.zero_()                                   # the call has consumed its source
+            assert first == n and np.array_equal(ix.read_rows_bf16(first, 64), want)
 
 
 def test_any_k_exact_scores_path_matches_oracle(rb, oracle_mod):

@@ -127,6 +127,37 @@ def test_vector_store_mutation_semantics(store):
     assert store.get_count() == 0 and store._index.size() == 0
 
 
+def test_re_embedded_document_is_two_engine_calls_and_equals_sequential_sets(store, tmp_path):
+    """addChunks over existing ids (vector-store.ts:135-183): the mirror issues ONE overwrite_f64_batch for the
+    re-sets and ONE append for the new ids, and ends in the same Map as set() item by item - also when an id occurs
+    twice in the batch (last value wins, position of the first occurrence)."""
+    from runbookai_b200 import embedder
+    from runbookai_b200.vector_store import VectorStore
+    store.add_chunks(_chunks(6, "docA"))
+    ix = store._index
+    slots_before = dict(store._slot_of)
+    ix.calls = 0
+    again = _chunks(6, "docA", text="kafka consumer lag rebalance") + _chunks(3, "docB")
+    again.append(_chunks(1, "docB", text="kafka broker down")[0])        # docB_0 a second time, other text
+    store.add_chunks(again)
+    assert ix.calls == 1                                                # one batch call for the six re-sets
+    assert {v: s for v, s in store._slot_of.items() if v in slots_before} == slots_before
+    assert [store._slot_of[f"vec_docB_{i}"] for i in range(3)] == [6, 7, 8] and ix.size() == 9
+    # the same sequence, one set at a time, in a second store
+    (tmp_path / "seq").mkdir()
+    other = VectorStore(str(tmp_path / "seq" / "vectors.db"), index_factory=lambda dim, dev: OracleIndex(dim))
+    try:
+        other.add_chunks(_chunks(6, "docA"))
+        for c in again:
+            other.add_chunk(c["chunk"], c["documentTitle"], c["type"], c["services"])
+        assert other._slot_of == store._slot_of and other._ids == store._ids
+        assert np.array_equal(other._index.rows, store._index.rows)
+        q = "kafka broker down"
+        assert other.search(q, {"minScore": 0.1}) == store.search(q, {"minScore": 0.1})
+    finally:
+        other.close()
+
+
 def test_vector_store_reload_is_rowid_order_and_errors(tmp_path):
     from runbookai_b200 import embedder
     from runbookai_b200.vector_store import VectorStore
