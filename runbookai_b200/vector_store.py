@@ -30,6 +30,7 @@ rewritten at close().  RUNBOOK_KNN_SIDECAR=0 turns it off.
 """
 from __future__ import annotations
 
+import hashlib
 import json
 import os
 import sqlite3
@@ -61,7 +62,11 @@ SCHEMA = """
 """
 NOT_CONFIGURED = "Embedder not configured. Set OPENAI_API_KEY."
 SIDECAR_MAGIC = b"RBKVEC1\0"
-_SIDECAR_HDR = struct.Struct("<8sIIQQQQ")   # magic, version, dim, rows, table count, max rowid, bytes of the id table
+# magic, version, dim, rows, table count, max rowid, generation (PRAGMA user_version), hash of the table's tail,
+# bytes of the id table
+_SIDECAR_HDR = struct.Struct("<8sIIQQQQQQ")
+_SIDECAR_VERSION = 2
+_TAIL_ROWS = 64
 
 
 @dataclass
@@ -205,9 +210,27 @@ class VectorStore:
         return self._index
 
     # ------------------------------------------------------------------ reload sidecar
-    def _fingerprint(self) -> tuple[int, int]:
+    def _fingerprint(self) -> tuple[int, int, int, int]:
+        """What a sidecar must match to be used: row count, highest rowid, the generation counter this class bumps
+        inside every mutating transaction (`PRAGMA user_version`: in the database header, transactional, unused by
+        the reference), and a hash of the ids and BLOBs of the last rows by rowid.  Count and rowid alone are not
+        enough: SQLite hands the rowid of a deleted LAST row out again, so re-embedding the newest chunk leaves both
+        unchanged.  The tail hash covers writers that do not know about the counter (the unpatched reference on the
+        same file), whose inserts and replacements land at the tail."""
         r = self.db.execute("SELECT COUNT(*), COALESCE(MAX(rowid), 0) FROM vector_embeddings").fetchone()
-        return int(r[0]), int(r[1])
+        gen = int(self.db.execute("PRAGMA user_version").fetchone()[0])
+        h = hashlib.blake2b(digest_size=8)
+        for row in self.db.execute("SELECT id, embedding FROM vector_embeddings ORDER BY rowid DESC LIMIT ?",
+                                   (_TAIL_ROWS,)):
+            h.update(row["id"].encode("utf-8"))
+            h.update(b"\0")
+            h.update(row["embedding"])
+        return int(r[0]), int(r[1]), gen, int.from_bytes(h.digest(), "little")
+
+    def _bump_generation(self) -> None:
+        """Inside the caller's transaction: the table is about to differ from every sidecar written so far."""
+        gen = int(self.db.execute("PRAGMA user_version").fetchone()[0])
+        self.db.execute(f"PRAGMA user_version = {(gen + 1) & 0x7FFFFFFF}")
 
     def _load_sidecar(self) -> bool:
         """Bulk-load from `<db>.rbk` if it describes the table as it is now."""
@@ -217,8 +240,9 @@ class VectorStore:
                 hdr = f.read(_SIDECAR_HDR.size)
                 if len(hdr) != _SIDECAR_HDR.size:
                     return False
-                magic, ver, dim, n, count, max_rowid, id_bytes = _SIDECAR_HDR.unpack(hdr)
-                if magic != SIDECAR_MAGIC or ver != 1 or (count, max_rowid) != self._fingerprint() or n != count:
+                magic, ver, dim, n, count, max_rowid, gen, tail, id_bytes = _SIDECAR_HDR.unpack(hdr)
+                if (magic != SIDECAR_MAGIC or ver != _SIDECAR_VERSION or n != count
+                        or (count, max_rowid, gen, tail) != self._fingerprint()):
                     return False
                 off = (_SIDECAR_HDR.size + id_bytes + 63) // 64 * 64
                 if os.path.getsize(path) != off + n * dim * 8:
@@ -250,7 +274,7 @@ class VectorStore:
         if not self._sidecar:
             return False
         with self._db_lock:
-            count, max_rowid = self._fingerprint()
+            count, max_rowid, gen, tail = self._fingerprint()
             cur = self.db.execute("SELECT id, embedding FROM vector_embeddings ORDER BY rowid")
             first = cur.fetchone()
             dim = len(first["embedding"]) // 8 if first else 0
@@ -275,7 +299,8 @@ class VectorStore:
                         rows = cur.fetchmany(4096)
                 idb = "\n".join(id_list).encode("utf-8")
                 f.seek(0)
-                f.write(_SIDECAR_HDR.pack(SIDECAR_MAGIC, 1, dim, len(id_list), count, max_rowid, len(idb)))
+                f.write(_SIDECAR_HDR.pack(SIDECAR_MAGIC, _SIDECAR_VERSION, dim, len(id_list), count, max_rowid, gen, tail,
+                                          len(idb)))
                 f.write(idb)
                 f.write(b"\0" * ((_SIDECAR_HDR.size + len(idb) + 63) // 64 * 64 - _SIDECAR_HDR.size - len(idb)))
                 with open(blobs_path, "rb") as bf:
@@ -292,8 +317,9 @@ class VectorStore:
         try:
             with open(self._db_path + ".rbk", "rb") as f:
                 hdr = f.read(_SIDECAR_HDR.size)
-            magic, ver, _, _, count, max_rowid, _ = _SIDECAR_HDR.unpack(hdr)
-            return magic == SIDECAR_MAGIC and ver == 1 and (count, max_rowid) == self._fingerprint()
+            magic, ver, _, _, count, max_rowid, gen, tail, _ = _SIDECAR_HDR.unpack(hdr)
+            return (magic == SIDECAR_MAGIC and ver == _SIDECAR_VERSION
+                    and (count, max_rowid, gen, tail) == self._fingerprint())
         except (OSError, struct.error):
             return False
 
@@ -360,6 +386,7 @@ class VectorStore:
                                                float_array_to_buffer(embedding), chunk["content"],
                                                chunk.get("sectionTitle") or document_title, type,
                                                json.dumps(list(services), separators=(",", ":"))))
+                self._bump_generation()   # after the first statement: inside the transaction it opened
             self._set(vid, embedding)
 
     def add_chunks(self, chunks: Sequence[dict]) -> None:
@@ -380,6 +407,8 @@ class VectorStore:
                                                float_array_to_buffer(e), ch["content"],
                                                ch.get("sectionTitle") or c["documentTitle"], c["type"],
                                                json.dumps(list(c["services"]), separators=(",", ":"))))
+            if chunks:
+                self._bump_generation()
         self._set_many([(f"vec_{c['chunk']['id']}", e) for c, e in zip(chunks, embeddings)])
 
     def _set_many(self, items) -> None:
@@ -432,6 +461,7 @@ class VectorStore:
             self._index.tombstone(slots)
         with self.db:
             self.db.execute("DELETE FROM vector_embeddings WHERE document_id = ?", (document_id,))
+            self._bump_generation()
 
     def get_count(self) -> int:
         """vector-store.ts:302-307."""
@@ -447,6 +477,7 @@ class VectorStore:
         with self._st.lock, self._db_lock:
             with self.db:
                 self.db.execute("DELETE FROM vector_embeddings")
+                self._bump_generation()
             self._ids.clear()
             self._slot_of.clear()
             self._st.bad_ids.clear()

@@ -474,7 +474,31 @@ def test_reload_sidecar_is_used_when_current_and_ignored_when_stale(tmp_path):
     s3.close()
     s4 = mk()
     assert s4.loaded_from_sidecar and s4._index.size() == 6
-    s4.close()
+    # SQLite hands the rowids of deleted LAST rows out again: deleting the newest document and adding one of the same
+    # size leaves the row count and the highest rowid unchanged.  (a) through this class: the generation counter in
+    # the db header moves
+    fp = s4._fingerprint()
+    s4.delete_document("docA")
+    s4.add_chunks(_chunks(3, "docA", text="completely different words about dns"))
+    fp2 = s4._fingerprint()
+    assert fp2[:2] == fp[:2] and fp2[2] == fp[2] + 2 and fp2[3] != fp[3]
+    want4 = s4.search("completely different words about dns", {"minScore": 0.1})
+    s4.close()                                             # stale by generation -> rewritten
+    s4b = mk()
+    assert s4b.loaded_from_sidecar and s4b.search("completely different words about dns", {"minScore": 0.1}) == want4
+    s4b.close()
+    # (b) a foreign writer that knows nothing about the counter does the same: the tail hash catches it
+    db = sqlite3.connect(path)
+    blob = db.execute("SELECT embedding FROM vector_embeddings WHERE id = 'vec_docB_1'").fetchone()[0]
+    row = db.execute("SELECT * FROM vector_embeddings ORDER BY rowid DESC LIMIT 1").fetchone()
+    db.execute("DELETE FROM vector_embeddings WHERE id = ?", (row[0],))
+    db.execute("INSERT INTO vector_embeddings (id, chunk_id, document_id, embedding, content, title, type, services) "
+               "VALUES (?, ?, ?, ?, ?, ?, ?, ?)", (row[0], row[1], row[2], blob, row[4], row[5], row[6], row[7]))
+    db.commit()
+    db.close()
+    s4c = mk()
+    assert s4c._fingerprint()[:3] == fp2[:3] and not s4c.loaded_from_sidecar
+    s4c.close()
     os.environ["RUNBOOK_KNN_SIDECAR"] = "0"
     try:
         s5 = mk()
