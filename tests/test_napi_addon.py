@@ -18,11 +18,19 @@ import pytest
 from conftest import HAS_CUDA, ROOT
 
 
-def _builder():
-    spec = importlib.util.spec_from_file_location("rbk_napi_mock_build", ROOT / "napi" / "mock" / "build.py")
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+def _build_real():
+    return _load("rbk_napi_mock_build", ROOT / "napi" / "mock" / "build.py").build()
+
+
+def _build_shim():
+    return _load("rbk_napi_shim_build", ROOT / "tests" / "napi_shim" / "build.py").build()
 
 
 def _write_inputs(d: Path, devices, dim=96, n=3000, nq=9, k=24, min_score=0.05, seed=11):
@@ -78,7 +86,7 @@ def _check_outputs(d: Path, w, oracle_mod):
 
 
 def test_addon_links_against_the_library_and_its_constructor_throws_without_a_gpu(tmp_path, native):
-    exe = _builder().build("real")          # compiles with -Wall -Wextra -Werror; every C-ABI symbol it binds resolves
+    exe = _build_real()          # compiles with -Wall -Wextra -Werror; every C-ABI symbol it binds resolves
     _write_inputs(tmp_path, devices=[])
     r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True, timeout=120)
     if HAS_CUDA:
@@ -90,7 +98,7 @@ def test_addon_links_against_the_library_and_its_constructor_throws_without_a_gp
 
 @pytest.mark.parametrize("devices", [[], [0]], ids=["index", "group"])
 def test_addon_scenario_against_the_oracle_backed_stand_in(tmp_path, oracle_mod, devices):
-    exe = _builder().build("shim")
+    exe = _build_shim()
     w = _write_inputs(tmp_path, devices)
     r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr + ((tmp_path / "error.txt").read_text() if (tmp_path / "error.txt").exists() else "")
@@ -100,7 +108,7 @@ def test_addon_scenario_against_the_oracle_backed_stand_in(tmp_path, oracle_mod,
 @pytest.mark.gpu
 @pytest.mark.parametrize("devices", [[], [0]], ids=["index", "group"])
 def test_addon_scenario_on_the_gpu_matches_the_oracle(tmp_path, oracle_mod, native, devices):
-    exe = _builder().build("real")
+    exe = _build_real()
     w = _write_inputs(tmp_path, devices, n=6000, dim=200, nq=13, k=32)
     r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr + ((tmp_path / "error.txt").read_text() if (tmp_path / "error.txt").exists() else "")
