@@ -174,3 +174,60 @@ export class GpuEmbeddingIndex {
     this.idOfSlot[slot] = id;
   }
 }
+
+/**
+ * Query micro-batcher (SURVEY 8f-3): concurrent `best()` calls that arrive within `windowMs` share ONE device pass
+ * (`bestBatch`), and every caller gets exactly what its own `best()` would have returned - the pass fetches for the
+ * most demanding caller (largest limit, lowest minScore) and each caller's own `>= minScore` and cut are re-applied.
+ * runbookai_b200/batcher.py is the tested mirror of this class (same coalescing, same per-caller cut, same
+ * behaviour on close).  Callers whose limit exceeds one pass (112) go through on their own.
+ */
+export class SearchBatcher {
+  private queue: Array<{
+    query: number[];
+    limit: number;
+    minScore: number;
+    resolve: (r: ScoredId[]) => void;
+    reject: (e: unknown) => void;
+  }> = [];
+  private timer: ReturnType<typeof setTimeout> | null = null;
+  private closed = false;
+  batches = 0;
+
+  constructor(private index: GpuEmbeddingIndex, private windowMs = 2, private maxBatch = 256) {}
+
+  best(query: number[], limit: number, minScore: number): Promise<ScoredId[]> {
+    if (this.closed) return Promise.reject(new Error('batcher closed'));
+    if (limit > 112) return this.index.best(query, limit, minScore);
+    return new Promise((resolve, reject) => {
+      this.queue.push({ query, limit, minScore, resolve, reject });
+      if (this.queue.length >= this.maxBatch) this.flush();
+      else if (!this.timer) this.timer = setTimeout(() => this.flush(), this.windowMs);
+    });
+  }
+
+  close(): void {
+    this.closed = true;
+    if (this.timer) clearTimeout(this.timer);
+    this.timer = null;
+    for (const w of this.queue.splice(0)) w.reject(new Error('batcher closed'));
+  }
+
+  private flush(): void {
+    if (this.timer) clearTimeout(this.timer);
+    this.timer = null;
+    const batch = this.queue.splice(0, this.maxBatch);
+    if (batch.length === 0) return;
+    if (this.queue.length > 0) this.timer = setTimeout(() => this.flush(), 0);
+    const limit = Math.max(...batch.map((w) => w.limit));
+    const minScore = Math.min(...batch.map((w) => w.minScore));
+    this.batches++;
+    this.index
+      .bestBatch(batch.map((w) => w.query), limit, minScore)
+      .then((all) =>
+        batch.forEach((w, i) => w.resolve(all[i].filter((h) => h.score >= w.minScore).slice(0, w.limit))),
+      )
+      .catch((e) => batch.forEach((w) => w.reject(e))); // every waiter gets the error its own best() would have thrown
+  }
+}
+
